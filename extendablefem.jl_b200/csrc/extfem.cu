@@ -1,0 +1,1041 @@
+// extfem.cu -- C-ABI implementation of libextfem_cuda.so (see include/extfem_cuda.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <tuple>
+
+#include "common.cuh"
+#include "fe_tables.h"
+#include "gather.cuh"
+#include "kernels_generic.cuh"
+#include "pattern.cuh"
+#include "fastpath.cuh"
+#include "solver.cuh"
+
+namespace extfem {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Mesh {
+    int dim = 0;
+    long long ncells = 0, nnodes = 0;
+    DevBuf coords, cellnodes, regions, vol, geo;
+    bool geo_valid = false;
+};
+
+struct Space {
+    int mesh = -1, fetype = 0, order = 0, ncomp = 0, nscalar = 0, nd = 0;
+    long long ndofs = 0;
+    DevBuf celldofs, adjptr, adjcell, adjloc;
+    // host-supplied tables (EXTFEM_FE_TABULATED)
+    int tab_nq = 0;
+    DevBuf tab_vals, tab_grads;
+};
+
+struct Pattern {
+    std::vector<int> rowspaces, colspaces;
+    std::vector<long long> rowoff, coloff;     // size n+1
+    std::vector<int> rowlocoff;                // per row block: offset in the posmap row
+    std::vector<unsigned char> coupling;       // [c*nrow + r]
+    int NRpat = 0;
+    long long nrows = 0, ncols = 0, nnz = 0;
+    int poswidth = 1;                          // bytes per posmap entry
+    int maxcollen = 0;
+    DevBuf colptr, rowval, nzval, b;
+    std::vector<std::unique_ptr<DevBuf>> posmap; // per column block
+    DevBuf chunkptr;
+    int nchunks = 0;
+    bool square = false;
+    SolverWork cg;
+};
+
+struct TableKey {
+    int dim, order, quadorder;
+    bool operator<(const TableKey &o) const { return std::tie(dim, order, quadorder) < std::tie(o.dim, o.order, o.quadorder); }
+};
+struct DevTables {
+    int nq = 0;
+    DevBuf vals, grads;
+};
+struct DevQuad {
+    int nq = 0;
+    DevBuf w, x;
+    std::vector<double> hw, hx;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::vector<std::unique_ptr<Mesh>> meshes;
+    std::vector<std::unique_ptr<Space>> spaces;
+    std::vector<std::unique_ptr<Pattern>> patterns;
+    std::map<TableKey, std::unique_ptr<DevTables>> tables;
+    std::map<std::pair<int, int>, std::unique_ptr<DevQuad>> quads; // (dim, order)
+    DevBuf custom_qw, custom_qx;
+    DevBuf loc, bloc, sol, params_scratch, tab;
+    long long launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double last_ms[3] = {0, 0, 0};
+};
+
+static std::string g_last_error;
+
+void set_error(Ctx *ctx, int code, const std::string &msg)
+{
+    std::string m = "extfem error " + std::to_string(code) + ": " + msg;
+    if (ctx) ctx->err = m;
+    g_last_error = m;
+}
+
+static int fail(Ctx *ctx, int code, const std::string &msg)
+{
+    set_error(ctx, code, msg);
+    return code;
+}
+
+static int ensure(Ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (b.bytes >= bytes && b.p) return 0;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+    if (bytes == 0) bytes = 16;
+    EXTFEM_CUDA_CHECK(ctx, cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    return 0;
+}
+
+static inline unsigned nblocks(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+#define LAUNCHED(ctx) (++(ctx)->launches)
+
+// ---------------------------------------------------------------------------------------------
+static int upload(Ctx *ctx, DevBuf &dst, const void *src, size_t bytes)
+{
+    if (int rc = ensure(ctx, dst, bytes)) return rc;
+    if (bytes) EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyDefault, ctx->stream));
+    return 0;
+}
+
+static int upload_indices(Ctx *ctx, DevBuf &dst, const void *src, int index_bytes, long long n)
+{
+    // src may be host or device; stage raw bytes on the device, then convert to 0-based int32
+    DevBuf raw;
+    if (int rc = upload(ctx, raw, src, (size_t)n * index_bytes)) return rc;
+    if (int rc = ensure(ctx, dst, (size_t)n * sizeof(int))) return rc;
+    convert_index_kernel<<<nblocks(n, 256), 256, 0, ctx->stream>>>(raw.p, index_bytes, n, dst.as<int>());
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int build_adjacency(Ctx *ctx, Space &S, long long ncells)
+{
+    long long n = ncells * S.nd;
+    DevBuf keys, keys2, vals, vals2, tmp;
+    if (int rc = ensure(ctx, keys, n * 8)) return rc;
+    if (int rc = ensure(ctx, keys2, n * 8)) return rc;
+    if (int rc = ensure(ctx, vals, n)) return rc;
+    if (int rc = ensure(ctx, vals2, n)) return rc;
+    adj_keys_kernel<<<nblocks(n, 256), 256, 0, ctx->stream>>>(S.celldofs.as<int>(), n, S.nd,
+                                                              keys.as<unsigned long long>(), vals.as<unsigned char>());
+    LAUNCHED(ctx);
+    int cellbits = 1, dofbits = 1;
+    while ((1ll << cellbits) < ncells) ++cellbits;
+    while ((1ll << dofbits) < S.ndofs + 1) ++dofbits;
+    (void)cellbits;
+    size_t tmpbytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmpbytes, keys.as<unsigned long long>(), keys2.as<unsigned long long>(),
+                                    vals.as<unsigned char>(), vals2.as<unsigned char>(), n, 0, 32 + dofbits, ctx->stream);
+    if (int rc = ensure(ctx, tmp, tmpbytes)) return rc;
+    EXTFEM_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmpbytes, keys.as<unsigned long long>(),
+                                                           keys2.as<unsigned long long>(), vals.as<unsigned char>(),
+                                                           vals2.as<unsigned char>(), n, 0, 32 + dofbits, ctx->stream));
+    LAUNCHED(ctx);
+    if (int rc = ensure(ctx, S.adjptr, (S.ndofs + 1) * 8)) return rc;
+    if (int rc = ensure(ctx, S.adjcell, n * 4)) return rc;
+    if (int rc = ensure(ctx, S.adjloc, n)) return rc;
+    adj_ptr_kernel<<<nblocks(S.ndofs + 1, 256), 256, 0, ctx->stream>>>(keys2.as<unsigned long long>(), n, S.ndofs,
+                                                                       S.adjptr.as<long long>());
+    LAUNCHED(ctx);
+    adj_cells_kernel<<<nblocks(n, 256), 256, 0, ctx->stream>>>(keys2.as<unsigned long long>(), n, S.adjcell.as<int>());
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(S.adjloc.p, vals2.p, n, cudaMemcpyDeviceToDevice, ctx->stream));
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int get_quad(Ctx *ctx, int dim, int order, DevQuad **out)
+{
+    auto key = std::make_pair(dim, order);
+    auto it = ctx->quads.find(key);
+    if (it == ctx->quads.end()) {
+        QuadRule Q = quadrature_rule(dim, order);
+        auto dq = std::make_unique<DevQuad>();
+        dq->nq = Q.nq;
+        dq->hw = Q.w;
+        dq->hx = Q.x;
+        if (int rc = upload(ctx, dq->w, Q.w.data(), Q.w.size() * 8)) return rc;
+        if (int rc = upload(ctx, dq->x, Q.x.data(), Q.x.size() * 8)) return rc;
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        it = ctx->quads.emplace(key, std::move(dq)).first;
+    }
+    *out = it->second.get();
+    return 0;
+}
+
+static int get_tables(Ctx *ctx, int dim, int order, int quadkey, const QuadRule &Q, DevTables **out)
+{
+    TableKey key{dim, order, quadkey};
+    auto it = ctx->tables.find(key);
+    if (it == ctx->tables.end() || quadkey < 0) {
+        std::vector<double> v, g;
+        ref_basis(order, dim, Q, v, g);
+        auto dt = std::make_unique<DevTables>();
+        dt->nq = Q.nq;
+        if (int rc = upload(ctx, dt->vals, v.data(), v.size() * 8)) return rc;
+        if (int rc = upload(ctx, dt->grads, g.data(), g.size() * 8)) return rc;
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (it != ctx->tables.end()) ctx->tables.erase(it);
+        it = ctx->tables.emplace(key, std::move(dt)).first;
+    }
+    *out = it->second.get();
+    return 0;
+}
+
+static int oplen_of(int op, int ncomp, int dim)
+{
+    switch (op) {
+    case EXTFEM_OP_ID: return ncomp;
+    case EXTFEM_OP_GRAD: return ncomp * dim;
+    case EXTFEM_OP_DIV: return 1;
+    case EXTFEM_OP_SYMGRAD_VOIGT: return dim == 1 ? 1 : (dim == 2 ? 3 : 6);
+    }
+    return -1;
+}
+
+struct Prepared {
+    OpDev op;
+    Mesh *mesh = nullptr;
+    std::vector<int> testblocks, colblocks; // unique blocks (ascending)
+    std::vector<int> testlocoff, collocoff;  // operator-local offsets of these blocks
+    int quadorder = 0;
+};
+
+enum OpKind { KIND_BILINEAR = 0, KIND_LINEAR = 1, KIND_NONLINEAR = 2 };
+
+static bool kernel_known(int kind, int id)
+{
+    if (kind == KIND_BILINEAR) return id >= EXTFEM_BLK_STANDARD && id <= EXTFEM_BLK_CONVECT_ARGS;
+    if (kind == KIND_LINEAR) return id >= EXTFEM_LIN_CONSTANT_ONE && id <= EXTFEM_LIN_TABULATED;
+    return id >= EXTFEM_NL_NSE2D && id <= EXTFEM_NL_RCD;
+}
+
+static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const double *sol, Prepared &R)
+{
+    if (!d) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "opdesc is NULL");
+    if (kind == KIND_LINEAR && d->nargs > 0) {
+        if (d->kernel_id != EXTFEM_BLK_STANDARD)
+            return fail(ctx, EXTFEM_ERR_UNREGISTERED_KERNEL, "LinearOperator with args supports only the standard kernel");
+    } else if (!kernel_known(kind, d->kernel_id))
+        return fail(ctx, EXTFEM_ERR_UNREGISTERED_KERNEL,
+                    "kernel id " + std::to_string(d->kernel_id) + " is not in the registry of this operator type");
+    if (d->ntest < 1 || d->ntest > MAXARGS || d->nansatz < 0 || d->nansatz > MAXARGS || d->nargs < 0 || d->nargs > MAXARGS)
+        return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "number of operator arguments out of range");
+    if (kind == KIND_BILINEAR && d->nansatz < 1) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "BilinearOperator needs ansatz arguments");
+    if (kind == KIND_NONLINEAR && d->nargs < 1) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "NonlinearOperator needs args");
+    if (d->nparams > MAXPARAMS) return fail(ctx, EXTFEM_ERR_CAPACITY, "too many kernel parameters");
+    if (d->nregions > MAXREGIONS) return fail(ctx, EXTFEM_ERR_CAPACITY, "too many regions");
+    if ((d->nargs > 0) && !sol) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "operator with args needs a solution vector");
+
+    OpDev &op = R.op;
+    memset(&op, 0, sizeof(op));
+    Space &S0 = *ctx->spaces[P.rowspaces[0]];
+    Mesh &M = *ctx->meshes[S0.mesh];
+    R.mesh = &M;
+    op.dim = M.dim;
+    op.ncells = M.ncells;
+    op.coords = M.coords.as<double>();
+    op.cellnodes = M.cellnodes.as<int>();
+    op.cellregions = M.regions.as<int>();
+    op.cellvolumes = M.vol.as<double>();
+    op.ntest = d->ntest; op.nansatz = d->nansatz; op.nargs = d->nargs;
+    op.kernel_id = d->kernel_id;
+    op.nparams = d->nparams;
+    for (int i = 0; i < d->nparams; ++i) op.params[i] = d->params[i];
+    op.factor = d->factor; op.time = d->time; op.offdiag = d->symgrad_offdiag;
+    op.nregions = d->nregions;
+    for (int i = 0; i < d->nregions; ++i) op.regions[i] = d->regions[i];
+    op.lump = d->lump;
+    for (int i = 0; i < MAXARGS * MAXARGS; ++i) op.coupling[i] = 1;
+    if (d->coupling)
+        for (int i = 0; i < d->nansatz * d->ntest; ++i) op.coupling[i] = d->coupling[i];
+
+    // --- resolve spaces / polynomial orders
+    auto rowspace = [&](int b) -> Space * { return (b >= 0 && b < (int)P.rowspaces.size()) ? ctx->spaces[P.rowspaces[b]].get() : nullptr; };
+    auto colspace = [&](int b) -> Space * { return (b >= 0 && b < (int)P.colspaces.size()) ? ctx->spaces[P.colspaces[b]].get() : nullptr; };
+    int poly_t = 0, poly_a = 0, poly_g = 0;
+    auto poly = [&](Space *S, int o) { return S->order - (o == EXTFEM_OP_ID ? 0 : 1); };
+    for (int i = 0; i < d->ntest; ++i) {
+        Space *S = rowspace(d->test_block[i]);
+        if (!S) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "test block index out of range");
+        poly_t = std::max(poly_t, poly(S, d->test_op[i]));
+    }
+    for (int i = 0; i < d->nansatz; ++i) {
+        Space *S = colspace(d->ansatz_block[i]);
+        if (!S) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "ansatz block index out of range");
+        poly_a = std::max(poly_a, poly(S, d->ansatz_op[i]));
+    }
+    for (int i = 0; i < d->nargs; ++i) {
+        Space *S = colspace(d->args_block[i]);
+        if (!S) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "args block index out of range");
+        poly_g = std::max(poly_g, poly(S, d->args_op[i]));
+    }
+    // quadrature order (bilinear_operator.jl:728-734, linear_operator.jl:534-538 / :299-305,
+    // nonlinear_operator.jl:187-193)
+    int qo;
+    if (d->quadorder >= 0) qo = d->quadorder + d->bonus_quadorder;
+    else if (kind == KIND_BILINEAR) qo = poly_a + poly_t + d->bonus_quadorder;
+    else if (kind == KIND_LINEAR) qo = poly_t + (d->nargs > 0 ? poly_g : 0) + d->bonus_quadorder;
+    else qo = poly_g + poly_t + d->bonus_quadorder;
+    R.quadorder = qo;
+    QuadRule Q;
+    int quadkey = qo;
+    if (d->nq_custom > 0) {
+        if (!d->qweights || !d->qpoints) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "custom quadrature needs weights and points");
+        Q.dim = M.dim; Q.nq = d->nq_custom;
+        Q.w.assign(d->qweights, d->qweights + Q.nq);
+        Q.x.assign(d->qpoints, d->qpoints + (size_t)Q.nq * M.dim);
+        if (int rc = upload(ctx, ctx->custom_qw, Q.w.data(), Q.w.size() * 8)) return rc;
+        if (int rc = upload(ctx, ctx->custom_qx, Q.x.data(), Q.x.size() * 8)) return rc;
+        op.qw = ctx->custom_qw.as<double>(); op.qx = ctx->custom_qx.as<double>();
+        quadkey = -1;
+    } else {
+        DevQuad *dq;
+        if (int rc = get_quad(ctx, M.dim, qo, &dq)) return rc;
+        Q.dim = M.dim; Q.nq = dq->nq; Q.w = dq->hw; Q.x = dq->hx;
+        op.qw = dq->w.as<double>(); op.qx = dq->x.as<double>();
+    }
+    op.nq = Q.nq;
+
+    // --- unique blocks and operator-local layout
+    auto uniq = [](std::vector<int> v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); return v; };
+    std::vector<int> tb, cb;
+    for (int i = 0; i < d->ntest; ++i) tb.push_back(d->test_block[i]);
+    if (kind == KIND_NONLINEAR) for (int i = 0; i < d->nargs; ++i) cb.push_back(d->args_block[i]);
+    else for (int i = 0; i < d->nansatz; ++i) cb.push_back(d->ansatz_block[i]);
+    R.testblocks = uniq(tb);
+    R.colblocks = uniq(cb);
+    int NR = 0, NC = 0;
+    for (int b : R.testblocks) { R.testlocoff.push_back(NR); NR += rowspace(b)->nd; }
+    for (int b : R.colblocks) { R.collocoff.push_back(NC); NC += colspace(b)->nd; }
+    if (NR > MAXLOC || NC > MAXLOC) return fail(ctx, EXTFEM_ERR_CAPACITY, "operator-local matrix larger than MAXLOC");
+    op.NR = NR; op.NC = NC;
+    auto locoff_of = [&](const std::vector<int> &blocks, const std::vector<int> &offs, int b) {
+        for (size_t i = 0; i < blocks.size(); ++i) if (blocks[i] == b) return offs[i];
+        return -1;
+    };
+    auto fill_arg = [&](ArgDev &a, Space *S, int o, int block, int &opoff, int locoff, long long soloff) -> int {
+        if (S->fetype != EXTFEM_FE_H1P1 && S->fetype != EXTFEM_FE_H1P2)
+            return fail(ctx, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "only H1P1/H1P2 (H1Pk order<=2) are built in");
+        if (o < EXTFEM_OP_ID || o > EXTFEM_OP_SYMGRAD_VOIGT)
+            return fail(ctx, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "unsupported function operator");
+        a.ncomp = S->ncomp; a.nscalar = S->nscalar; a.op = o; a.nd = S->nd;
+        a.oplen = oplen_of(o, S->ncomp, M.dim);
+        a.opoff = opoff; opoff += a.oplen;
+        a.locoff = locoff; a.block = block;
+        a.celldofs = S->celldofs.as<int>();
+        a.soloff = soloff;
+        DevTables *T;
+        if (int rc = get_tables(ctx, M.dim, S->order, quadkey, Q, &T)) return rc;
+        a.refvals = T->vals.as<double>(); a.refgrads = T->grads.as<double>();
+        return 0;
+    };
+    int off_t = 0, off_a = 0, off_g = 0;
+    for (int i = 0; i < d->ntest; ++i)
+        if (int rc = fill_arg(op.test[i], rowspace(d->test_block[i]), d->test_op[i], d->test_block[i], off_t,
+                              locoff_of(R.testblocks, R.testlocoff, d->test_block[i]), 0)) return rc;
+    for (int i = 0; i < d->nansatz; ++i)
+        if (int rc = fill_arg(op.ansatz[i], colspace(d->ansatz_block[i]), d->ansatz_op[i], d->ansatz_block[i], off_a,
+                              locoff_of(R.colblocks, R.collocoff, d->ansatz_block[i]), 0)) return rc;
+    for (int i = 0; i < d->nargs; ++i)
+        if (int rc = fill_arg(op.args[i], colspace(d->args_block[i]), d->args_op[i], d->args_block[i], off_g,
+                              kind == KIND_NONLINEAR ? locoff_of(R.colblocks, R.collocoff, d->args_block[i]) : 0,
+                              P.coloff[d->args_block[i]])) return rc;
+    op.nout = off_t;
+    op.nin = (kind == KIND_BILINEAR && d->nargs == 0) ? off_a : off_g;
+    if (off_t > MAXOP || off_a > MAXOP || off_g > MAXOP) return fail(ctx, EXTFEM_ERR_CAPACITY, "operator vector longer than MAXOP");
+    // sanity of kernel shapes
+    if (kind == KIND_BILINEAR && d->kernel_id == EXTFEM_BLK_STANDARD && off_t != off_a)
+        return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "standard kernel needs equal operator lengths of test and ansatz");
+    if (kind == KIND_NONLINEAR && (d->kernel_id == EXTFEM_NL_NSE2D || d->kernel_id == EXTFEM_NL_LINNSE7) &&
+        (off_g != 7 || off_t != 7 || M.dim != 2))
+        return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "nse2d kernels need [id(u),grad(u),id(p)] in 2D");
+    if (kind == KIND_NONLINEAR && d->kernel_id == EXTFEM_NL_NEOHOOKE3D && (off_g != 9 || off_t != 9 || M.dim != 3))
+        return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "neohooke3d needs [grad(u)] in 3D");
+    if (sol) {
+        if (int rc = upload(ctx, ctx->sol, sol, (size_t)P.ncols * 8)) return rc;
+        op.sol = ctx->sol.as<double>();
+    }
+    if (kind == KIND_LINEAR && d->kernel_id == EXTFEM_LIN_TABULATED && d->nargs == 0) {
+        if (!d->tabulated) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "tabulated kernel needs values");
+        if (int rc = upload(ctx, ctx->tab, d->tabulated, (size_t)M.ncells * op.nq * op.nout * 8)) return rc;
+        op.tabulated = ctx->tab.as<double>();
+    }
+    return 0;
+}
+
+template <typename F>
+static int dispatch_dim(Ctx *ctx, int dim, F &&f)
+{
+    switch (dim) {
+    case 1: f(std::integral_constant<int, 1>{}); return 0;
+    case 2: f(std::integral_constant<int, 2>{}); return 0;
+    case 3: f(std::integral_constant<int, 3>{}); return 0;
+    }
+    return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "dim must be 1, 2 or 3");
+}
+
+static int cells_per_block(size_t per_cell_bytes)
+{
+    size_t budget = 40 * 1024;
+    int cpb = (int)(budget / per_cell_bytes);
+    return std::max(1, std::min(16, cpb));
+}
+
+// --- gather launches ---------------------------------------------------------------------------
+template <typename PosT>
+static int launch_gather_cols(Ctx *ctx, Pattern &P, const Prepared &R, int overwrite, int transposed, double scale)
+{
+    GatherArgs<PosT> g;
+    memset(&g, 0, sizeof(g));
+    g.chunkptr = P.chunkptr.as<int>();
+    g.colptr = P.colptr.as<long long>();
+    g.nzval = P.nzval.as<double>();
+    g.ncb = (int)P.colspaces.size();
+    for (int c = 0; c <= g.ncb; ++c) g.coloff[c] = P.coloff[c];
+    g.NRpat = P.NRpat; g.NRop = R.op.NR; g.NCop = R.op.NC;
+    g.loc = ctx->loc.as<double>();
+    g.overwrite = overwrite; g.transposed = transposed; g.scale = scale;
+    const std::vector<int> &colside = transposed ? R.testblocks : R.colblocks;
+    const std::vector<int> &colsideoff = transposed ? R.testlocoff : R.collocoff;
+    const std::vector<int> &rowside = transposed ? R.colblocks : R.testblocks;
+    const std::vector<int> &rowsideoff = transposed ? R.collocoff : R.testlocoff;
+    for (int c = 0; c < g.ncb; ++c) {
+        Space &S = *ctx->spaces[P.colspaces[c]];
+        g.adjptr[c] = S.adjptr.as<long long>(); g.adjcell[c] = S.adjcell.as<int>(); g.adjloc[c] = S.adjloc.as<unsigned char>();
+        g.posmap[c] = P.posmap[c]->as<PosT>();
+        g.collocoff[c] = -1; g.colnd[c] = S.nd;
+        for (size_t i = 0; i < colside.size(); ++i) if (colside[i] == c) g.collocoff[c] = colsideoff[i];
+    }
+    int t = 0;
+    for (size_t i = 0; i < rowside.size(); ++i) {
+        int b = rowside[i];
+        if (b >= (int)P.rowspaces.size()) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "transposed copy needs a square block system");
+        int nd = ctx->spaces[P.rowspaces[b]]->nd;
+        for (int j = 0; j < nd; ++j, ++t) { g.rowmap[t] = P.rowlocoff[b] + j; g.rowsrc[t] = rowsideoff[i] + j; }
+    }
+    g.nrows_g = t;
+    gather_columns_kernel<PosT><<<P.nchunks, GATHER_THREADS, 0, ctx->stream>>>(g);
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+static int gather_matrix(Ctx *ctx, Pattern &P, const Prepared &R, int accumulate, int transposed_copy)
+{
+    int rc = P.poswidth == 1 ? launch_gather_cols<unsigned char>(ctx, P, R, !accumulate, 0, 1.0)
+                             : launch_gather_cols<unsigned short>(ctx, P, R, !accumulate, 0, 1.0);
+    if (rc) return rc;
+    if (transposed_copy != 0) {
+        if (!P.square) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "transposed_copy needs a square block system");
+        rc = P.poswidth == 1 ? launch_gather_cols<unsigned char>(ctx, P, R, 0, 1, (double)transposed_copy)
+                             : launch_gather_cols<unsigned short>(ctx, P, R, 0, 1, (double)transposed_copy);
+    }
+    return rc;
+}
+
+static int gather_vector(Ctx *ctx, Pattern &P, const Prepared &R, int accumulate)
+{
+    GatherVecArgs g;
+    memset(&g, 0, sizeof(g));
+    g.nrb = (int)P.rowspaces.size();
+    for (int r = 0; r <= g.nrb; ++r) g.rowoff[r] = P.rowoff[r];
+    for (int r = 0; r < g.nrb; ++r) {
+        Space &S = *ctx->spaces[P.rowspaces[r]];
+        g.adjptr[r] = S.adjptr.as<long long>(); g.adjcell[r] = S.adjcell.as<int>(); g.adjloc[r] = S.adjloc.as<unsigned char>();
+        g.rowlocoff[r] = -1;
+        for (size_t i = 0; i < R.testblocks.size(); ++i) if (R.testblocks[i] == r) g.rowlocoff[r] = R.testlocoff[i];
+    }
+    g.NRop = R.op.NR; g.bloc = ctx->bloc.as<double>(); g.b = P.b.as<double>(); g.overwrite = !accumulate; g.nrows = P.nrows;
+    gather_rows_kernel<<<nblocks(P.nrows, 256), 256, 0, ctx->stream>>>(g);
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+static int finish_timing(Ctx *ctx)
+{
+    EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&c, ctx->ev[0], ctx->ev[3]);
+    ctx->last_ms[0] = a; ctx->last_ms[1] = b; ctx->last_ms[2] = c;
+    return 0;
+}
+
+// fast paths for the headline configurations; *fast == false -> generic path
+static int try_fast_bilinear(Ctx *, Pattern &, const Prepared &, const extfem_opdesc *, int, bool *fast)
+{
+    *fast = false;
+    return 0;
+}
+
+} // namespace extfem
+
+using namespace extfem;
+
+#define CTX_GUARD(ctx)                                                                  \
+    if (!(ctx)) { set_error(nullptr, EXTFEM_ERR_BAD_ARGUMENT, "ctx is NULL"); return EXTFEM_ERR_BAD_ARGUMENT; } \
+    Ctx *C = reinterpret_cast<Ctx *>(ctx);                                              \
+    cudaSetDevice(C->device);
+
+#define GET_PATTERN(id)                                                                 \
+    if ((id) < 0 || (id) >= (int)C->patterns.size() || !C->patterns[id])                \
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "invalid pattern handle");             \
+    Pattern &P = *C->patterns[id];
+
+extern "C" {
+
+int extfem_ctx_create(int device, extfem_ctx **out)
+{
+    if (!out) return fail(nullptr, EXTFEM_ERR_BAD_ARGUMENT, "out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, EXTFEM_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                                  cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, EXTFEM_ERR_BAD_ARGUMENT, "device index out of range");
+    Ctx *C = new Ctx();
+    C->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&C->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete C;
+        return fail(nullptr, EXTFEM_ERR_CUDA, "cannot initialise device");
+    }
+    for (auto &ev : C->ev) cudaEventCreate(&ev);
+    *out = reinterpret_cast<extfem_ctx *>(C);
+    return EXTFEM_OK;
+}
+
+int extfem_ctx_destroy(extfem_ctx *ctx)
+{
+    if (!ctx) return EXTFEM_OK;
+    Ctx *C = reinterpret_cast<Ctx *>(ctx);
+    cudaSetDevice(C->device);
+    cudaStreamSynchronize(C->stream);
+    for (auto &ev : C->ev) if (ev) cudaEventDestroy(ev);
+    C->patterns.clear(); C->spaces.clear(); C->meshes.clear();
+    cudaStream_t s = C->stream;
+    delete C;
+    cudaStreamDestroy(s);
+    return EXTFEM_OK;
+}
+
+const char *extfem_last_error(extfem_ctx *ctx)
+{
+    if (ctx) return reinterpret_cast<Ctx *>(ctx)->err.c_str();
+    return g_last_error.c_str();
+}
+
+int extfem_kernel_id(const char *name)
+{
+    static const struct { const char *n; int id; } tab[] = {
+        {"standard", EXTFEM_BLK_STANDARD}, {"dcr", EXTFEM_BLK_DCR}, {"stokes", EXTFEM_BLK_STOKES},
+        {"linnse7", EXTFEM_BLK_LINNSE7}, {"hooke_grad", EXTFEM_BLK_HOOKE_GRAD}, {"hooke_voigt", EXTFEM_BLK_HOOKE_VOIGT},
+        {"convect_args", EXTFEM_BLK_CONVECT_ARGS},
+        {"constant_one", EXTFEM_LIN_CONSTANT_ONE}, {"constant_params", EXTFEM_LIN_CONSTANT_PARAMS}, {"xy", EXTFEM_LIN_XY},
+        {"sincos301", EXTFEM_LIN_SINCOS301}, {"tabulated", EXTFEM_LIN_TABULATED},
+        {"nse2d", EXTFEM_NL_NSE2D}, {"nl_linnse7", EXTFEM_NL_LINNSE7}, {"neohooke3d", EXTFEM_NL_NEOHOOKE3D}, {"rcd", EXTFEM_NL_RCD}};
+    if (name)
+        for (auto &t : tab) if (!strcmp(t.n, name)) return t.id;
+    set_error(nullptr, EXTFEM_ERR_UNREGISTERED_KERNEL, std::string("kernel '") + (name ? name : "(null)") + "' is not registered");
+    return EXTFEM_ERR_UNREGISTERED_KERNEL;
+}
+
+int extfem_synchronize(extfem_ctx *ctx)
+{
+    CTX_GUARD(ctx);
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    return EXTFEM_OK;
+}
+
+int64_t extfem_launch_count(extfem_ctx *ctx) { return ctx ? reinterpret_cast<Ctx *>(ctx)->launches : 0; }
+
+int extfem_last_timings(extfem_ctx *ctx, double *ms3)
+{
+    CTX_GUARD(ctx);
+    for (int i = 0; i < 3; ++i) ms3[i] = C->last_ms[i];
+    return EXTFEM_OK;
+}
+
+int extfem_mesh_set(extfem_ctx *ctx, int dim, int64_t ncells, int64_t nnodes, const double *coords, const void *cellnodes,
+                    int index_bytes, const int32_t *cellregions, const double *cellvolumes, int *mesh_out)
+{
+    CTX_GUARD(ctx);
+    if (dim < 1 || dim > 3 || ncells <= 0 || nnodes <= 0 || !coords || !cellnodes || !mesh_out || (index_bytes != 4 && index_bytes != 8))
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_mesh_set: bad argument");
+    if (ncells >= (1ll << 31) || nnodes >= (1ll << 31)) return fail(C, EXTFEM_ERR_CAPACITY, "mesh too large for 32-bit device indices");
+    auto M = std::make_unique<Mesh>();
+    M->dim = dim; M->ncells = ncells; M->nnodes = nnodes;
+    if (int rc = upload(C, M->coords, coords, (size_t)nnodes * dim * 8)) return rc;
+    if (int rc = upload_indices(C, M->cellnodes, cellnodes, index_bytes, ncells * (dim + 1))) return rc;
+    if (cellregions) { if (int rc = upload(C, M->regions, cellregions, (size_t)ncells * 4)) return rc; }
+    else {
+        std::vector<int> ones((size_t)ncells, 1);
+        if (int rc = upload(C, M->regions, ones.data(), (size_t)ncells * 4)) return rc;
+        EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    }
+    if (int rc = ensure(C, M->vol, (size_t)ncells * 8)) return rc;
+    if (cellvolumes) { EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(M->vol.p, cellvolumes, (size_t)ncells * 8, cudaMemcpyDefault, C->stream)); }
+    else {
+        if (int rc = launch_cell_volumes(C->stream, dim, ncells, M->coords.as<double>(), M->cellnodes.as<int>(), M->vol.as<double>()))
+            return fail(C, EXTFEM_ERR_CUDA, "cell volume kernel failed");
+        LAUNCHED(C);
+    }
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    C->meshes.push_back(std::move(M));
+    *mesh_out = (int)C->meshes.size() - 1;
+    return EXTFEM_OK;
+}
+
+int extfem_mesh_update_coords(extfem_ctx *ctx, int mesh, const double *coords, const double *cellvolumes)
+{
+    CTX_GUARD(ctx);
+    if (mesh < 0 || mesh >= (int)C->meshes.size() || !coords) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "invalid mesh handle");
+    Mesh &M = *C->meshes[mesh];
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(M.coords.p, coords, (size_t)M.nnodes * M.dim * 8, cudaMemcpyDefault, C->stream));
+    if (cellvolumes) { EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(M.vol.p, cellvolumes, (size_t)M.ncells * 8, cudaMemcpyDefault, C->stream)); }
+    else {
+        launch_cell_volumes(C->stream, M.dim, M.ncells, M.coords.as<double>(), M.cellnodes.as<int>(), M.vol.as<double>());
+        LAUNCHED(C);
+    }
+    M.geo_valid = false;
+    return EXTFEM_OK;
+}
+
+int extfem_space_set(extfem_ctx *ctx, int mesh, int fetype, int ncomp, const void *celldofs, int index_bytes, int ndofs4cell,
+                     int64_t ndofs, int *space_out)
+{
+    CTX_GUARD(ctx);
+    if (mesh < 0 || mesh >= (int)C->meshes.size() || !celldofs || !space_out || ncomp < 1 || (index_bytes != 4 && index_bytes != 8))
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_space_set: bad argument");
+    Mesh &M = *C->meshes[mesh];
+    int order = fetype == EXTFEM_FE_H1P1 ? 1 : (fetype == EXTFEM_FE_H1P2 ? 2 : -1);
+    if (order < 0)
+        return fail(C, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "fetype " + std::to_string(fetype) + " is not supported (H1P1, H1P2 / H1Pk order<=2)");
+    int ns = nscalar_of(order, M.dim);
+    if (ndofs4cell != ns * ncomp)
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "ndofs4cell does not match the element (expected " + std::to_string(ns * ncomp) + ")");
+    if (ndofs4cell > 255) return fail(C, EXTFEM_ERR_CAPACITY, "ndofs4cell > 255");
+    if (ndofs >= (1ll << 31)) return fail(C, EXTFEM_ERR_CAPACITY, "too many dofs for 32-bit device indices");
+    auto S = std::make_unique<Space>();
+    S->mesh = mesh; S->fetype = fetype; S->order = order; S->ncomp = ncomp; S->nscalar = ns; S->nd = ndofs4cell; S->ndofs = ndofs;
+    if (int rc = upload_indices(C, S->celldofs, celldofs, index_bytes, M.ncells * ndofs4cell)) return rc;
+    if (int rc = build_adjacency(C, *S, M.ncells)) return rc;
+    C->spaces.push_back(std::move(S));
+    *space_out = (int)C->spaces.size() - 1;
+    return EXTFEM_OK;
+}
+
+int extfem_space_set_tables(extfem_ctx *ctx, int, int, int, const double *, const double *)
+{
+    CTX_GUARD(ctx);
+    return fail(C, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "host-tabulated elements are not implemented yet");
+}
+
+int extfem_pattern_build(extfem_ctx *ctx, int nrow, const int *rowspaces, int ncol, const int *colspaces,
+                         const uint8_t *block_coupling, int *pattern_out)
+{
+    CTX_GUARD(ctx);
+    if (nrow < 1 || ncol < 1 || nrow > MAXBLOCKS || ncol > MAXBLOCKS || !rowspaces || !colspaces || !pattern_out)
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_pattern_build: bad argument");
+    auto Pp = std::make_unique<Pattern>();
+    Pattern &P = *Pp;
+    int mesh = -1;
+    P.rowoff.push_back(0); P.coloff.push_back(0);
+    for (int r = 0; r < nrow; ++r) {
+        int s = rowspaces[r];
+        if (s < 0 || s >= (int)C->spaces.size()) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "invalid row space handle");
+        if (mesh < 0) mesh = C->spaces[s]->mesh;
+        if (C->spaces[s]->mesh != mesh) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "all spaces of a pattern must live on one mesh");
+        P.rowspaces.push_back(s);
+        P.rowlocoff.push_back(P.NRpat);
+        P.NRpat += C->spaces[s]->nd;
+        P.rowoff.push_back(P.rowoff.back() + C->spaces[s]->ndofs);
+    }
+    for (int c = 0; c < ncol; ++c) {
+        int s = colspaces[c];
+        if (s < 0 || s >= (int)C->spaces.size()) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "invalid column space handle");
+        if (C->spaces[s]->mesh != mesh) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "all spaces of a pattern must live on one mesh");
+        P.colspaces.push_back(s);
+        P.coloff.push_back(P.coloff.back() + C->spaces[s]->ndofs);
+    }
+    P.nrows = P.rowoff.back(); P.ncols = P.coloff.back();
+    if (P.nrows >= (1ll << 31) - 1) return fail(C, EXTFEM_ERR_CAPACITY, "too many rows for 32-bit row indices");
+    P.square = (P.rowspaces == P.colspaces);
+    P.coupling.assign((size_t)ncol * nrow, 1);
+    if (block_coupling) for (int i = 0; i < ncol * nrow; ++i) P.coupling[i] = block_coupling[i] ? 1 : 0;
+    Mesh &M = *C->meshes[mesh];
+    (void)M;
+
+    DevBuf collen, err, tmp;
+    if (int rc = ensure(C, collen, (P.ncols + 1) * 8)) return rc;
+    if (int rc = ensure(C, err, 4)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaMemsetAsync(collen.p, 0, (P.ncols + 1) * 8, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaMemsetAsync(err.p, 0, 4, C->stream));
+    std::vector<PatArgs> pargs(ncol);
+    for (int c = 0; c < ncol; ++c) {
+        Space &Sc = *C->spaces[P.colspaces[c]];
+        PatArgs &A = pargs[c];
+        memset(&A, 0, sizeof(A));
+        A.ncolsb = Sc.ndofs; A.colbase = P.coloff[c];
+        A.adjptr = Sc.adjptr.as<long long>(); A.adjcell = Sc.adjcell.as<int>();
+        A.nrb = nrow; A.NRpat = P.NRpat; A.error = err.as<int>();
+        for (int r = 0; r < nrow; ++r) {
+            Space &Sr = *C->spaces[P.rowspaces[r]];
+            A.coupled[r] = P.coupling[(size_t)c * nrow + r];
+            A.celldofs[r] = Sr.celldofs.as<int>(); A.nd[r] = Sr.nd; A.rowoff[r] = P.rowoff[r]; A.rowlocoff[r] = P.rowlocoff[r];
+        }
+        pattern_count_kernel<<<nblocks(Sc.ndofs, PAT_WARPS), PAT_WARPS * 32, 0, C->stream>>>(A, collen.as<long long>());
+        LAUNCHED(C);
+    }
+    EXTFEM_CUDA_CHECK(C, cudaGetLastError());
+    int herr = 0;
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(&herr, err.p, 4, cudaMemcpyDeviceToHost, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    if (herr) return fail(C, EXTFEM_ERR_CAPACITY, "a matrix column has more than " + std::to_string(PAT_CAP) + " candidate rows");
+    // max column length -> width of the position map
+    {
+        DevBuf dmax;
+        if (int rc = ensure(C, dmax, 8)) return rc;
+        size_t tb = 0;
+        cub::DeviceReduce::Max(nullptr, tb, collen.as<long long>(), dmax.as<long long>(), (int)(P.ncols), C->stream);
+        if (int rc = ensure(C, tmp, tb)) return rc;
+        EXTFEM_CUDA_CHECK(C, cub::DeviceReduce::Max(tmp.p, tb, collen.as<long long>(), dmax.as<long long>(), (long long)P.ncols, C->stream));
+        LAUNCHED(C);
+        long long hmax = 0;
+        EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(&hmax, dmax.p, 8, cudaMemcpyDeviceToHost, C->stream));
+        EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+        P.maxcollen = (int)hmax;
+        P.poswidth = hmax <= 254 ? 1 : 2;
+        if (hmax > 65534 || hmax > GATHER_MAXNNZ) return fail(C, EXTFEM_ERR_CAPACITY, "matrix column too long");
+    }
+    if (int rc = ensure(C, P.colptr, (P.ncols + 1) * 8)) return rc;
+    {
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, collen.as<long long>(), P.colptr.as<long long>(), (long long)(P.ncols + 1), C->stream);
+        DevBuf t2;
+        if (int rc = ensure(C, t2, tb)) return rc;
+        EXTFEM_CUDA_CHECK(C, cub::DeviceScan::ExclusiveSum(t2.p, tb, collen.as<long long>(), P.colptr.as<long long>(),
+                                                           (long long)(P.ncols + 1), C->stream));
+        LAUNCHED(C);
+        EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    }
+    std::vector<long long> hcolptr((size_t)P.ncols + 1);
+    EXTFEM_CUDA_CHECK(C, cudaMemcpy(hcolptr.data(), P.colptr.p, (P.ncols + 1) * 8, cudaMemcpyDeviceToHost));
+    P.nnz = hcolptr.back();
+    if (int rc = ensure(C, P.rowval, (size_t)P.nnz * 4)) return rc;
+    if (int rc = ensure(C, P.nzval, (size_t)P.nnz * 8)) return rc;
+    if (int rc = ensure(C, P.b, (size_t)P.nrows * 8)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaMemsetAsync(P.nzval.p, 0, (size_t)P.nnz * 8, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaMemsetAsync(P.b.p, 0, (size_t)P.nrows * 8, C->stream));
+    for (int c = 0; c < ncol; ++c) {
+        Space &Sc = *C->spaces[P.colspaces[c]];
+        long long npairs = M.ncells * Sc.nd;
+        P.posmap.push_back(std::make_unique<DevBuf>());
+        if (int rc = ensure(C, *P.posmap.back(), (size_t)npairs * P.NRpat * P.poswidth)) return rc;
+        if (P.poswidth == 1)
+            pattern_fill_kernel<unsigned char><<<nblocks(Sc.ndofs, PAT_WARPS), PAT_WARPS * 32, 0, C->stream>>>(
+                pargs[c], P.colptr.as<long long>(), P.rowval.as<int>(), P.posmap.back()->as<unsigned char>());
+        else
+            pattern_fill_kernel<unsigned short><<<nblocks(Sc.ndofs, PAT_WARPS), PAT_WARPS * 32, 0, C->stream>>>(
+                pargs[c], P.colptr.as<long long>(), P.rowval.as<int>(), P.posmap.back()->as<unsigned short>());
+        LAUNCHED(C);
+    }
+    EXTFEM_CUDA_CHECK(C, cudaGetLastError());
+    // column chunks of the gather kernel: <= GATHER_THREADS columns, <= GATHER_MAXNNZ entries, one column block
+    std::vector<int> chunks;
+    chunks.push_back(0);
+    for (int c = 0; c < ncol; ++c) {
+        long long k = P.coloff[c], kend = P.coloff[c + 1];
+        while (k < kend) {
+            long long k2 = k;
+            long long base = hcolptr[k];
+            while (k2 < kend && k2 - k < GATHER_THREADS && hcolptr[k2 + 1] - base <= GATHER_MAXNNZ) ++k2;
+            if (k2 == k) return fail(C, EXTFEM_ERR_CAPACITY, "matrix column too long for the gather kernel");
+            chunks.push_back((int)k2);
+            k = k2;
+        }
+    }
+    P.nchunks = (int)chunks.size() - 1;
+    if (int rc = upload(C, P.chunkptr, chunks.data(), chunks.size() * 4)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    C->patterns.push_back(std::move(Pp));
+    *pattern_out = (int)C->patterns.size() - 1;
+    return EXTFEM_OK;
+}
+
+int extfem_pattern_dims(extfem_ctx *ctx, int pattern, int64_t *nrows, int64_t *ncols, int64_t *nnz)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (nrows) *nrows = P.nrows;
+    if (ncols) *ncols = P.ncols;
+    if (nnz) *nnz = P.nnz;
+    return EXTFEM_OK;
+}
+
+int extfem_pattern_get(extfem_ctx *ctx, int pattern, int64_t *colptr, int64_t *rowval)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    DevBuf c64, r64;
+    if (colptr) if (int rc = ensure(C, c64, (P.ncols + 1) * 8)) return rc;
+    if (rowval) if (int rc = ensure(C, r64, (size_t)P.nnz * 8)) return rc;
+    long long n = std::max(P.ncols + 1, P.nnz);
+    csc_export_kernel<<<nblocks(n, 256), 256, 0, C->stream>>>(P.colptr.as<long long>(), P.ncols + 1, P.rowval.as<int>(), P.nnz,
+                                                              colptr ? c64.as<long long>() : nullptr, rowval ? r64.as<long long>() : nullptr);
+    LAUNCHED(C);
+    if (colptr) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(colptr, c64.p, (P.ncols + 1) * 8, cudaMemcpyDefault, C->stream));
+    if (rowval) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(rowval, r64.p, (size_t)P.nnz * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    return EXTFEM_OK;
+}
+
+int extfem_assemble_bilinear(extfem_ctx *ctx, int pattern, const extfem_opdesc *d, const double *sol, int accumulate, double *nzval_out)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    Prepared R;
+    if (int rc = prepare(C, P, d, KIND_BILINEAR, d && d->nargs > 0 ? sol : nullptr, R)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[0], C->stream));
+    bool fast = false;
+    if (int rc = try_fast_bilinear(C, P, R, d, accumulate, &fast)) return rc;
+    if (!fast) {
+        const OpDev &op = R.op;
+        if (int rc = ensure(C, C->loc, (size_t)op.ncells * op.NR * op.NC * 8)) return rc;
+        int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
+            constexpr int DIM = decltype(dimc)::value;
+            size_t per_cell = sizeof(CellGeo<DIM>) + (op.nargs > 0 ? (size_t)op.nq * op.nin * 8 : 0);
+            int cpb = cells_per_block(per_cell);
+            local_bilinear_kernel<DIM><<<nblocks(op.ncells, cpb), 256, cpb * per_cell, C->stream>>>(op, C->loc.as<double>(), cpb);
+        });
+        if (rcd) return rcd;
+        LAUNCHED(C);
+        EXTFEM_CUDA_CHECK(C, cudaGetLastError());
+        EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[1], C->stream));
+        if (int rc = gather_matrix(C, P, R, accumulate, d->transposed_copy)) return rc;
+        EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[2], C->stream));
+    }
+    if (nzval_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(nzval_out, P.nzval.p, (size_t)P.nnz * 8, cudaMemcpyDefault, C->stream));
+    return finish_timing(C);
+}
+
+int extfem_assemble_linear(extfem_ctx *ctx, int pattern, const extfem_opdesc *d, const double *sol, int accumulate, double *b_out)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    Prepared R;
+    if (int rc = prepare(C, P, d, KIND_LINEAR, d && d->nargs > 0 ? sol : nullptr, R)) return rc;
+    const OpDev &op = R.op;
+    if (int rc = ensure(C, C->bloc, (size_t)op.ncells * op.NR * 8)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[0], C->stream));
+    int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
+        constexpr int DIM = decltype(dimc)::value;
+        size_t per_cell = sizeof(CellGeo<DIM>) + (size_t)op.nq * op.nout * 8;
+        int cpb = cells_per_block(per_cell);
+        local_linear_kernel<DIM><<<nblocks(op.ncells, cpb), 256, cpb * per_cell, C->stream>>>(op, C->bloc.as<double>(), cpb);
+    });
+    if (rcd) return rcd;
+    LAUNCHED(C);
+    EXTFEM_CUDA_CHECK(C, cudaGetLastError());
+    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[1], C->stream));
+    if (int rc = gather_vector(C, P, R, accumulate)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[2], C->stream));
+    if (b_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b_out, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    return finish_timing(C);
+}
+
+int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc *d, const double *sol, int accumulate,
+                              double *nzval_out, double *b_out)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    Prepared R;
+    if (int rc = prepare(C, P, d, KIND_NONLINEAR, sol, R)) return rc;
+    const OpDev &op = R.op;
+    if (int rc = ensure(C, C->loc, (size_t)op.ncells * op.NR * op.NC * 8)) return rc;
+    if (int rc = ensure(C, C->bloc, (size_t)op.ncells * op.NR * 8)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[0], C->stream));
+    int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
+        constexpr int DIM = decltype(dimc)::value;
+        size_t per_cell = sizeof(CellGeo<DIM>) + (size_t)op.nq * (op.nout * op.nin + op.nout) * 8;
+        int cpb = cells_per_block(per_cell);
+        local_nonlinear_kernel<DIM><<<nblocks(op.ncells, cpb), 256, cpb * per_cell, C->stream>>>(op, C->loc.as<double>(),
+                                                                                               C->bloc.as<double>(), cpb);
+    });
+    if (rcd) return rcd;
+    LAUNCHED(C);
+    EXTFEM_CUDA_CHECK(C, cudaGetLastError());
+    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[1], C->stream));
+    if (int rc = gather_matrix(C, P, R, accumulate, 0)) return rc;
+    if (int rc = gather_vector(C, P, R, accumulate)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[2], C->stream));
+    if (nzval_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(nzval_out, P.nzval.p, (size_t)P.nnz * 8, cudaMemcpyDefault, C->stream));
+    if (b_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b_out, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    return finish_timing(C);
+}
+
+int extfem_quadrature_points(extfem_ctx *ctx, int pattern, const extfem_opdesc *d, int is_linear, int *nq_out, double *xq)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    Prepared R;
+    extfem_opdesc dd = *d;
+    if (is_linear && dd.kernel_id == EXTFEM_LIN_TABULATED) dd.kernel_id = EXTFEM_LIN_CONSTANT_ONE; // values not needed here
+    if (int rc = prepare(C, P, &dd, is_linear ? KIND_LINEAR : KIND_BILINEAR, nullptr, R)) return rc;
+    if (nq_out) *nq_out = R.op.nq;
+    if (!xq) return EXTFEM_OK;
+    const OpDev &op = R.op;
+    DevBuf dx;
+    long long n = op.ncells * op.nq;
+    if (int rc = ensure(C, dx, (size_t)n * op.dim * 8)) return rc;
+    int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
+        constexpr int DIM = decltype(dimc)::value;
+        quadpoints_kernel<DIM><<<nblocks(n, 256), 256, 0, C->stream>>>(op, dx.as<double>());
+    });
+    if (rcd) return rcd;
+    LAUNCHED(C);
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(xq, dx.p, (size_t)n * op.dim * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    return EXTFEM_OK;
+}
+
+int extfem_values_get(extfem_ctx *ctx, int pattern, double *nzval, double *b)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (nzval) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(nzval, P.nzval.p, (size_t)P.nnz * 8, cudaMemcpyDefault, C->stream));
+    if (b) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    return EXTFEM_OK;
+}
+
+int extfem_values_set(extfem_ctx *ctx, int pattern, const double *nzval, const double *b)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (nzval) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(P.nzval.p, nzval, (size_t)P.nnz * 8, cudaMemcpyDefault, C->stream));
+    if (b) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(P.b.p, b, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    return EXTFEM_OK;
+}
+
+int extfem_device_ptrs(extfem_ctx *ctx, int pattern, void **colptr, void **rowval, void **nzval, void **b)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (colptr) *colptr = P.colptr.p;
+    if (rowval) *rowval = P.rowval.p;
+    if (nzval) *nzval = P.nzval.p;
+    if (b) *b = P.b.p;
+    return EXTFEM_OK;
+}
+
+int extfem_apply_penalties(extfem_ctx *ctx, int pattern, int64_t ndofs, const int64_t *dofs, const double *values, double penalty)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (ndofs == 0) return EXTFEM_OK;
+    if (!dofs) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "dofs is NULL");
+    DevBuf dd, dv;
+    if (int rc = upload(C, dd, dofs, (size_t)ndofs * 8)) return rc;
+    if (values) if (int rc = upload(C, dv, values, (size_t)ndofs * 8)) return rc;
+    DevBuf err;
+    if (int rc = ensure(C, err, 4)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaMemsetAsync(err.p, 0, 4, C->stream));
+    penalties_kernel<<<nblocks(ndofs, 256), 256, 0, C->stream>>>(ndofs, dd.as<long long>(), values ? dv.as<double>() : nullptr, penalty,
+                                                                P.colptr.as<long long>(), P.rowval.as<int>(), P.nzval.as<double>(),
+                                                                P.b.as<double>(), P.nrows, err.as<int>());
+    LAUNCHED(C);
+    int herr = 0;
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(&herr, err.p, 4, cudaMemcpyDeviceToHost, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    if (herr) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "penalty dof out of range or without diagonal entry");
+    return EXTFEM_OK;
+}
+
+int extfem_spmv(extfem_ctx *ctx, int pattern, const double *x, double *y)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (!x || !y) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "x or y is NULL");
+    DevBuf dx, dy;
+    if (int rc = upload(C, dx, x, (size_t)P.ncols * 8)) return rc;
+    if (int rc = ensure(C, dy, (size_t)P.nrows * 8)) return rc;
+    if (int rc = csc_spmv(C->stream, P.nrows, P.ncols, P.nnz, P.colptr.as<long long>(), P.rowval.as<int>(), P.nzval.as<double>(),
+                          dx.as<double>(), dy.as<double>(), P.cg, &C->launches))
+        return fail(C, EXTFEM_ERR_CUDA, "spmv failed");
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(y, dy.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    return EXTFEM_OK;
+}
+
+int extfem_residual(extfem_ctx *ctx, int pattern, const double *sol, double *res_out)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (!sol || !res_out) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "sol or res_out is NULL");
+    DevBuf dx, dy;
+    if (int rc = upload(C, dx, sol, (size_t)P.ncols * 8)) return rc;
+    if (int rc = ensure(C, dy, (size_t)P.nrows * 8)) return rc;
+    if (int rc = csc_spmv(C->stream, P.nrows, P.ncols, P.nnz, P.colptr.as<long long>(), P.rowval.as<int>(), P.nzval.as<double>(),
+                          dx.as<double>(), dy.as<double>(), P.cg, &C->launches))
+        return fail(C, EXTFEM_ERR_CUDA, "spmv failed");
+    residual_kernel<<<nblocks(P.nrows, 256), 256, 0, C->stream>>>(P.nrows, P.b.as<double>(), dy.as<double>());
+    LAUNCHED(C);
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(res_out, dy.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    return EXTFEM_OK;
+}
+
+int extfem_cg(extfem_ctx *ctx, int pattern, const double *b, double *x, double rtol, int maxit, int *iters, double *relres)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (!P.square || P.nrows != P.ncols) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "CG needs a square system");
+    if (!x) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "x is NULL");
+    DevBuf db, dx;
+    const double *bptr = P.b.as<double>();
+    if (b) { if (int rc = upload(C, db, b, (size_t)P.nrows * 8)) return rc; bptr = db.as<double>(); }
+    if (int rc = upload(C, dx, x, (size_t)P.nrows * 8)) return rc;
+    int it = 0; double rr = 0;
+    if (int rc = jacobi_cg(C->stream, P.nrows, P.nnz, P.colptr.as<long long>(), P.rowval.as<int>(), P.nzval.as<double>(), bptr,
+                           dx.as<double>(), rtol, maxit, &it, &rr, P.cg, &C->launches))
+        return fail(C, EXTFEM_ERR_CUDA, "CG failed (CUDA error or breakdown), code " + std::to_string(rc));
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(x, dx.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    if (iters) *iters = it;
+    if (relres) *relres = rr;
+    return EXTFEM_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,566 @@
+// kernels_generic.cuh -- generic (any registered kernel / element / block layout) local
+// assembly kernels.  One CTA processes CPB consecutive cells cooperatively:
+//
+//   phase A  per (cell, qp)   : affine geometry, x_q, solution evaluation, kernel Jacobian /
+//                                source value  -> shared memory                     (staging)
+//   phase B  per local entry  : quadrature contraction with on-the-fly basis evaluation,
+//                                written to the cell-local buffer with unit-stride stores
+//
+// The cell-local buffer is then reduced into the CSC values by the column-gather kernel
+// (gather.cuh) without atomics.  These kernels restate the loop nests
+//   bilinear_operator.jl:876-916 / :512-561, linear_operator.jl:619-637 / :408-435,
+//   nonlinear_operator.jl:343-415
+// with the quadrature index innermost per entry (summation order over qp is preserved).
+#pragma once
+#include "common.cuh"
+
+namespace extfem {
+
+// sparse operator evaluation of one basis function at one quadrature point: cvals[:, j, qp]
+struct CV {
+    int idx[3];
+    double v[3];
+    int len;
+};
+
+template <int DIM>
+__device__ __forceinline__ CV eval_cv(const ArgDev &a, int j, int q, const double *__restrict__ Ainv, double offdiag)
+{
+    CV cv;
+    int c = j / a.nscalar, k = j - c * a.nscalar;
+    if (a.op == EXTFEM_OP_ID) {
+        cv.len = 1;
+        cv.idx[0] = c;
+        cv.v[0] = __ldg(a.refvals + q * a.nscalar + k);
+        return cv;
+    }
+    double g[DIM];
+    const double *rg = a.refgrads + ((size_t)q * a.nscalar + k) * DIM;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        double s = 0;
+#pragma unroll
+        for (int r = 0; r < DIM; ++r) s += Ainv[r * DIM + d] * __ldg(rg + r);
+        g[d] = s;
+    }
+    if (a.op == EXTFEM_OP_GRAD) {
+        cv.len = DIM;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { cv.idx[d] = c * DIM + d; cv.v[d] = g[d]; }
+    } else if (a.op == EXTFEM_OP_DIV) {
+        cv.len = 1;
+        cv.idx[0] = 0;
+        cv.v[0] = g[c < DIM ? c : 0];
+    } else { // SYMGRAD_VOIGT
+        if (DIM == 1) { cv.len = 1; cv.idx[0] = 0; cv.v[0] = g[0]; }
+        else if (DIM == 2) {
+            cv.len = 2;
+            cv.idx[0] = c; cv.v[0] = g[c];
+            cv.idx[1] = 2; cv.v[1] = offdiag * g[(1 - c) & 1];
+        } else {
+            cv.len = 3;
+            cv.idx[0] = c; cv.v[0] = g[c];
+            // Voigt order 23, 13, 12
+            int o1 = (c == 0) ? 4 : 3, o2 = (c == 2) ? 4 : 5;
+            int g1 = (c == 0) ? 2 : ((c == 1) ? 2 : 1), g2 = (c == 0) ? 1 : 0;
+            cv.idx[1] = o1; cv.v[1] = offdiag * g[g1 < DIM ? g1 : 0];
+            cv.idx[2] = o2; cv.v[2] = offdiag * g[g2 < DIM ? g2 : 0];
+        }
+    }
+    return cv;
+}
+
+// ---- registry: bilinear kernels (linear in `in`) ------------------------------------------
+__device__ __forceinline__ void bl_apply(int id, int dim, const double *in, const double *ain, const double *p,
+                                         double *r, int nout)
+{
+    switch (id) {
+    case EXTFEM_BLK_STANDARD:
+        for (int d = 0; d < nout; ++d) r[d] = in[d];
+        break;
+    case EXTFEM_BLK_DCR: {
+        double s = p[0] * in[0];
+        for (int d = 0; d < dim; ++d) s += p[2 + d] * in[1 + d];
+        r[0] = s;
+        for (int d = 0; d < dim; ++d) r[1 + d] = p[1] * in[1 + d];
+    } break;
+    case EXTFEM_BLK_STOKES: {
+        int n = dim * dim;
+        double div = 0;
+        for (int d = 0; d < n; ++d) r[d] = p[0] * in[d];
+        for (int c = 0; c < dim; ++c) { r[c * dim + c] -= in[n]; div += in[c * dim + c]; }
+        r[n] = -div;
+    } break;
+    case EXTFEM_BLK_LINNSE7: {
+        const double *u = in, *g = in + 2;
+        double pr = in[6], mu = p[0], al = p[1];
+        r[0] = g[0] + al * u[0];
+        r[1] = g[2] + al * u[1];
+        r[2] = mu * g[0] - pr;
+        r[3] = mu * g[1];
+        r[4] = mu * g[2];
+        r[5] = mu * g[3] - pr;
+        r[6] = -(g[0] + g[3]);
+    } break;
+    case EXTFEM_BLK_HOOKE_GRAD: {
+        double mu = p[0], la = p[1], tr = 0;
+        for (int c = 0; c < dim; ++c) tr += in[c * dim + c];
+        for (int c = 0; c < dim; ++c)
+            for (int d = 0; d < dim; ++d)
+                r[c * dim + d] = mu * (in[c * dim + d] + in[d * dim + c]) + (c == d ? la * tr : 0.0);
+    } break;
+    case EXTFEM_BLK_HOOKE_VOIGT:
+        for (int i = 0; i < nout; ++i) {
+            double s = 0;
+            for (int j = 0; j < nout; ++j) s += p[i * nout + j] * in[j];
+            r[i] = s;
+        }
+        break;
+    case EXTFEM_BLK_CONVECT_ARGS:
+        for (int c = 0; c < nout; ++c) {
+            double s = 0;
+            for (int d = 0; d < dim; ++d) s += ain[d] * in[c * dim + d];
+            r[c] = s;
+        }
+        break;
+    }
+}
+
+__device__ __forceinline__ void lin_apply(int id, const double *x, const double *p, double *r, int nout,
+                                          const double *tab)
+{
+    switch (id) {
+    case EXTFEM_LIN_CONSTANT_ONE: for (int d = 0; d < nout; ++d) r[d] = 1.0; break;
+    case EXTFEM_LIN_CONSTANT_PARAMS: for (int d = 0; d < nout; ++d) r[d] = p[d]; break;
+    case EXTFEM_LIN_XY: r[0] = x[0] * x[1]; break;
+    case EXTFEM_LIN_SINCOS301: r[0] = p[0] * (1.7 * 1.7 + 3.9 * 3.9) * sin(1.7 * x[0]) * cos(3.9 * x[1]); break;
+    case EXTFEM_LIN_TABULATED: for (int d = 0; d < nout; ++d) r[d] = tab[d]; break;
+    }
+}
+
+// ---- registry: nonlinear kernels with analytic Jacobians ----------------------------------
+// value[nout], jac[nout][nin] (row-major, written densely)
+__device__ __forceinline__ void nl_apply(int id, int dim, const double *in, const double *p, double *val, double *J,
+                                         int nin, int nout)
+{
+    for (int i = 0; i < nin * nout; ++i) J[i] = 0.0;
+    switch (id) {
+    case EXTFEM_NL_NSE2D: {
+        const double *u = in, *g = in + 2;
+        double pr = in[6], mu = p[0];
+        val[0] = g[0] * u[0] + g[1] * u[1];
+        val[1] = g[2] * u[0] + g[3] * u[1];
+        val[2] = mu * g[0] - pr;
+        val[3] = mu * g[1];
+        val[4] = mu * g[2];
+        val[5] = mu * g[3] - pr;
+        val[6] = -(g[0] + g[3]);
+        J[0 * 7 + 0] = g[0]; J[0 * 7 + 1] = g[1]; J[0 * 7 + 2] = u[0]; J[0 * 7 + 3] = u[1];
+        J[1 * 7 + 0] = g[2]; J[1 * 7 + 1] = g[3]; J[1 * 7 + 4] = u[0]; J[1 * 7 + 5] = u[1];
+        J[2 * 7 + 2] = mu; J[2 * 7 + 6] = -1.0;
+        J[3 * 7 + 3] = mu;
+        J[4 * 7 + 4] = mu;
+        J[5 * 7 + 5] = mu; J[5 * 7 + 6] = -1.0;
+        J[6 * 7 + 2] = -1.0; J[6 * 7 + 5] = -1.0;
+    } break;
+    case EXTFEM_NL_LINNSE7: {
+        const double *u = in, *g = in + 2;
+        double pr = in[6], mu = p[0], al = p[1];
+        val[0] = g[0] + al * u[0];
+        val[1] = g[2] + al * u[1];
+        val[2] = mu * g[0] - pr;
+        val[3] = mu * g[1];
+        val[4] = mu * g[2];
+        val[5] = mu * g[3] - pr;
+        val[6] = -(g[0] + g[3]);
+        J[0 * 7 + 2] = 1.0; J[0 * 7 + 0] = al;
+        J[1 * 7 + 4] = 1.0; J[1 * 7 + 1] = al;
+        J[2 * 7 + 2] = mu; J[2 * 7 + 6] = -1.0;
+        J[3 * 7 + 3] = mu;
+        J[4 * 7 + 4] = mu;
+        J[5 * 7 + 5] = mu; J[5 * 7 + 6] = -1.0;
+        J[6 * 7 + 2] = -1.0; J[6 * 7 + 5] = -1.0;
+    } break;
+    case EXTFEM_NL_NEOHOOKE3D: {
+        // DW = mu F + c * dd,  c = (lambda log(det) - mu)/det,  dd = d det / dF
+        // D2W = mu I + c * d(dd)/dF + dd (x) dd * (lambda + mu - lambda log(det)) / det^2
+        double mu = p[0], la = p[1];
+        double F[9];
+        for (int i = 0; i < 9; ++i) F[i] = in[i];
+        F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
+        double dd[9];
+        dd[0] = F[4] * F[8] - F[5] * F[7];
+        dd[1] = F[5] * F[6] - F[3] * F[8];
+        dd[2] = F[3] * F[7] - F[4] * F[6];
+        dd[3] = F[2] * F[7] - F[1] * F[8];
+        dd[4] = F[0] * F[8] - F[2] * F[6];
+        dd[5] = F[1] * F[6] - F[0] * F[7];
+        dd[6] = F[1] * F[5] - F[2] * F[4];
+        dd[7] = F[2] * F[3] - F[0] * F[5];
+        dd[8] = F[0] * F[4] - F[1] * F[3];
+        double det = F[0] * dd[0] + F[1] * dd[1] + F[2] * dd[2];
+        double ld = log(det);
+        double c = (la * ld - mu) / det;
+        double e = (la + mu - la * ld) / (det * det);
+        for (int i = 0; i < 9; ++i) val[i] = mu * F[i] + c * dd[i];
+        for (int i = 0; i < 9; ++i) {
+            for (int j = 0; j < 9; ++j) J[i * 9 + j] = e * dd[i] * dd[j];
+            J[i * 9 + i] += mu;
+        }
+        // c * d(dd_i)/dF_j : dd is the cofactor matrix, its derivative is +-F entries
+#define EXTFEM_D2(i, j, s, k) J[(i) * 9 + (j)] += (s) * c * F[k];
+        EXTFEM_D2(0, 4, 1, 8) EXTFEM_D2(0, 8, 1, 4) EXTFEM_D2(0, 5, -1, 7) EXTFEM_D2(0, 7, -1, 5)
+        EXTFEM_D2(1, 5, 1, 6) EXTFEM_D2(1, 6, 1, 5) EXTFEM_D2(1, 3, -1, 8) EXTFEM_D2(1, 8, -1, 3)
+        EXTFEM_D2(2, 3, 1, 7) EXTFEM_D2(2, 7, 1, 3) EXTFEM_D2(2, 4, -1, 6) EXTFEM_D2(2, 6, -1, 4)
+        EXTFEM_D2(3, 2, 1, 7) EXTFEM_D2(3, 7, 1, 2) EXTFEM_D2(3, 1, -1, 8) EXTFEM_D2(3, 8, -1, 1)
+        EXTFEM_D2(4, 0, 1, 8) EXTFEM_D2(4, 8, 1, 0) EXTFEM_D2(4, 2, -1, 6) EXTFEM_D2(4, 6, -1, 2)
+        EXTFEM_D2(5, 1, 1, 6) EXTFEM_D2(5, 6, 1, 1) EXTFEM_D2(5, 0, -1, 7) EXTFEM_D2(5, 7, -1, 0)
+        EXTFEM_D2(6, 1, 1, 5) EXTFEM_D2(6, 5, 1, 1) EXTFEM_D2(6, 2, -1, 4) EXTFEM_D2(6, 4, -1, 2)
+        EXTFEM_D2(7, 2, 1, 3) EXTFEM_D2(7, 3, 1, 2) EXTFEM_D2(7, 0, -1, 5) EXTFEM_D2(7, 5, -1, 0)
+        EXTFEM_D2(8, 0, 1, 4) EXTFEM_D2(8, 4, 1, 0) EXTFEM_D2(8, 1, -1, 3) EXTFEM_D2(8, 3, -1, 1)
+#undef EXTFEM_D2
+    } break;
+    case EXTFEM_NL_RCD: {
+        val[0] = in[0] * in[1] + in[0];
+        J[0 * nin + 0] = in[1] + 1.0;
+        J[0 * nin + 1] = in[0];
+        for (int d = 0; d < dim; ++d) { val[1 + d] = in[1 + d]; J[(1 + d) * nin + 1 + d] = 1.0; }
+    } break;
+    }
+}
+
+// ---- shared-memory cell slot ------------------------------------------------------------------
+template <int DIM>
+struct CellGeo {
+    double Ainv[DIM * DIM];
+    double A[DIM * DIM];
+    double x0[DIM];
+    double vol;
+    int visited;
+    int pad;
+};
+
+template <int DIM>
+__device__ __forceinline__ void load_geo(const OpDev &op, long long cell, CellGeo<DIM> &G)
+{
+    const int *cn = op.cellnodes + cell * (DIM + 1);
+    const double *p0 = op.coords + (size_t)cn[0] * DIM;
+    double A[DIM][DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) G.x0[d] = p0[d];
+#pragma unroll
+    for (int r = 0; r < DIM; ++r) {
+        const double *pr = op.coords + (size_t)cn[r + 1] * DIM;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) A[d][r] = pr[d] - p0[d];
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+        for (int r = 0; r < DIM; ++r) G.A[d * DIM + r] = A[d][r];
+    if (DIM == 1) {
+        G.Ainv[0] = 1.0 / A[0][0];
+    } else if (DIM == 2) {
+        double det = A[0][0] * A[1 % DIM][1 % DIM] - A[0][1 % DIM] * A[1 % DIM][0];
+        double id = 1.0 / det;
+        G.Ainv[0 * DIM + 0] = A[1 % DIM][1 % DIM] * id;
+        G.Ainv[0 * DIM + 1 % DIM] = -A[0][1 % DIM] * id;
+        G.Ainv[(1 % DIM) * DIM + 0] = -A[1 % DIM][0] * id;
+        G.Ainv[(1 % DIM) * DIM + 1 % DIM] = A[0][0] * id;
+    } else {
+        constexpr int I1 = 1 % DIM, I2 = 2 % DIM;
+        double c00 = A[I1][I1] * A[I2][I2] - A[I1][I2] * A[I2][I1];
+        double c01 = A[I1][I2] * A[I2][0] - A[I1][0] * A[I2][I2];
+        double c02 = A[I1][0] * A[I2][I1] - A[I1][I1] * A[I2][0];
+        double det = A[0][0] * c00 + A[0][I1] * c01 + A[0][I2] * c02;
+        double id = 1.0 / det;
+        G.Ainv[0 * DIM + 0] = c00 * id;
+        G.Ainv[I1 * DIM + 0] = c01 * id;
+        G.Ainv[I2 * DIM + 0] = c02 * id;
+        G.Ainv[0 * DIM + I1] = (A[0][I2] * A[I2][I1] - A[0][I1] * A[I2][I2]) * id;
+        G.Ainv[I1 * DIM + I1] = (A[0][0] * A[I2][I2] - A[0][I2] * A[I2][0]) * id;
+        G.Ainv[I2 * DIM + I1] = (A[0][I1] * A[I2][0] - A[0][0] * A[I2][I1]) * id;
+        G.Ainv[0 * DIM + I2] = (A[0][I1] * A[I1][I2] - A[0][I2] * A[I1][I1]) * id;
+        G.Ainv[I1 * DIM + I2] = (A[0][I2] * A[I1][0] - A[0][0] * A[I1][I2]) * id;
+        G.Ainv[I2 * DIM + I2] = (A[0][0] * A[I1][I1] - A[0][I1] * A[I1][0]) * id;
+    }
+    G.vol = op.cellvolumes[cell];
+    int reg = op.cellregions[cell];
+    int vis = 1;
+    if (op.nregions > 0) {
+        vis = 0;
+        for (int k = 0; k < op.nregions; ++k) vis |= (op.regions[k] == reg);
+    }
+    G.visited = vis;
+}
+
+template <int DIM>
+__device__ __forceinline__ void eval_x(const CellGeo<DIM> &G, const double *xref, double *x)
+{
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        double s = G.x0[d];
+#pragma unroll
+        for (int r = 0; r < DIM; ++r) s += G.A[d * DIM + r] * xref[r];
+        x[d] = s;
+    }
+}
+
+// input_args[q] = sum_j sol[dof_j] * cvals[:, j, q]   (bilinear_operator.jl:513-521)
+template <int DIM>
+__device__ __forceinline__ void eval_args(const OpDev &op, long long cell, int q, const CellGeo<DIM> &G, double *u)
+{
+    for (int d = 0; d < op.nin; ++d) u[d] = 0.0;
+    for (int id = 0; id < op.nargs; ++id) {
+        const ArgDev &a = op.args[id];
+        const int *dofs = a.celldofs + cell * a.nd;
+        for (int j = 0; j < a.nd; ++j) {
+            double s = op.sol[a.soloff + dofs[j]];
+            CV cv = eval_cv<DIM>(a, j, q, G.Ainv, op.offdiag);
+            for (int t = 0; t < cv.len; ++t) u[a.opoff + cv.idx[t]] += s * cv.v[t];
+        }
+    }
+}
+
+__device__ __forceinline__ const ArgDev *find_arg(const ArgDev *args, int n, int loc, int &jj, int from)
+{
+    // arguments whose block covers local index `loc`; iterate with `from`
+    for (int i = from; i < n; ++i)
+        if (loc >= args[i].locoff && loc < args[i].locoff + args[i].nd) { jj = loc - args[i].locoff; return &args[i]; }
+    return nullptr;
+}
+
+// =============================== BilinearOperator ==============================================
+template <int DIM>
+__global__ void __launch_bounds__(256)
+local_bilinear_kernel(const __grid_constant__ OpDev op, double *__restrict__ loc, int CPB)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CellGeo<DIM> *geo = reinterpret_cast<CellGeo<DIM> *>(smem_raw);
+    double *uq = reinterpret_cast<double *>(geo + CPB); // [CPB][nq][nin_args] when nargs > 0
+    const int nin_args = op.nargs > 0 ? op.nin : 0;
+    long long c0 = (long long)blockIdx.x * CPB;
+    int ncell = (int)min((long long)CPB, op.ncells - c0);
+    for (int s = threadIdx.x; s < ncell; s += blockDim.x) load_geo<DIM>(op, c0 + s, geo[s]);
+    __syncthreads();
+    if (op.nargs > 0) {
+        for (int t = threadIdx.x; t < ncell * op.nq; t += blockDim.x) {
+            int s = t / op.nq, q = t - s * op.nq;
+            double u[MAXOP];
+            eval_args<DIM>(op, c0 + s, q, geo[s], u);
+            for (int d = 0; d < nin_args; ++d) uq[(size_t)t * nin_args + d] = u[d];
+        }
+        __syncthreads();
+    }
+    const int NRC = op.NR * op.NC;
+    // ansatz-vector length when kernel has args: the kernel input is the ansatz evaluation
+    int nin_a = 0;
+    for (int i = 0; i < op.nansatz; ++i) nin_a = max(nin_a, op.ansatz[i].opoff + op.ansatz[i].oplen);
+    for (int e = threadIdx.x; e < ncell * NRC; e += blockDim.x) {
+        int s = e / NRC, r = e - s * NRC;
+        int j = r / op.NR, k = r - j * op.NR;
+        const CellGeo<DIM> &G = geo[s];
+        double acc = 0.0;
+        if (G.visited) {
+            for (int id = 0; id < op.nansatz; ++id) {
+                const ArgDev &aa = op.ansatz[id];
+                if (j < aa.locoff || j >= aa.locoff + aa.nd) continue;
+                int jj = j - aa.locoff;
+                for (int idt = 0; idt < op.ntest; ++idt) {
+                    const ArgDev &ta = op.test[idt];
+                    if (k < ta.locoff || k >= ta.locoff + ta.nd) continue;
+                    int kk = k - ta.locoff;
+                    if (op.lump) { if (idt != id || kk != jj) continue; }
+                    else if (!op.coupling[id * op.ntest + idt]) continue;
+                    double a = 0.0;
+                    for (int q = 0; q < op.nq; ++q) {
+                        CV ca = eval_cv<DIM>(aa, jj, q, G.Ainv, op.offdiag);
+                        double fw = op.factor * op.qw[q];
+                        if (op.kernel_id == EXTFEM_BLK_STANDARD) {
+                            // result = input: only matching slots of the operator vectors contribute
+                            if (op.lump == 2) {
+                                for (int k2 = 0; k2 < ta.nd; ++k2) {
+                                    CV ct = eval_cv<DIM>(ta, k2, q, G.Ainv, op.offdiag);
+                                    for (int t = 0; t < ct.len; ++t)
+                                        for (int t2 = 0; t2 < ca.len; ++t2)
+                                            if (ct.idx[t] + ta.opoff == ca.idx[t2] + aa.opoff) a += (ca.v[t2] * fw) * ct.v[t];
+                                }
+                            } else {
+                                CV ct = eval_cv<DIM>(ta, kk, q, G.Ainv, op.offdiag);
+                                for (int t = 0; t < ct.len; ++t)
+                                    for (int t2 = 0; t2 < ca.len; ++t2)
+                                        if (ct.idx[t] + ta.opoff == ca.idx[t2] + aa.opoff) a += (ca.v[t2] * fw) * ct.v[t];
+                            }
+                        } else {
+                            double in[MAXOP], res[MAXOP];
+                            for (int d = 0; d < MAXOP; ++d) in[d] = 0.0;
+                            for (int t2 = 0; t2 < ca.len; ++t2) in[aa.opoff + ca.idx[t2]] = ca.v[t2];
+                            const double *ain = op.nargs > 0 ? uq + ((size_t)s * op.nq + q) * nin_args : nullptr;
+                            bl_apply(op.kernel_id, DIM, in, ain, op.params, res, op.nout);
+                            if (op.lump == 2) {
+                                for (int k2 = 0; k2 < ta.nd; ++k2) {
+                                    CV ct = eval_cv<DIM>(ta, k2, q, G.Ainv, op.offdiag);
+                                    for (int t = 0; t < ct.len; ++t) a += (res[ta.opoff + ct.idx[t]] * fw) * ct.v[t];
+                                }
+                            } else {
+                                CV ct = eval_cv<DIM>(ta, kk, q, G.Ainv, op.offdiag);
+                                for (int t = 0; t < ct.len; ++t) a += (res[ta.opoff + ct.idx[t]] * fw) * ct.v[t];
+                            }
+                        }
+                    }
+                    acc += a * G.vol;
+                }
+            }
+        }
+        loc[(size_t)(c0 + s) * NRC + r] = acc;
+    }
+    (void)nin_a;
+}
+
+// =============================== LinearOperator ================================================
+template <int DIM>
+__global__ void __launch_bounds__(256)
+local_linear_kernel(const __grid_constant__ OpDev op, double *__restrict__ bloc, int CPB)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CellGeo<DIM> *geo = reinterpret_cast<CellGeo<DIM> *>(smem_raw);
+    double *fq = reinterpret_cast<double *>(geo + CPB); // [CPB][nq][nout]
+    long long c0 = (long long)blockIdx.x * CPB;
+    int ncell = (int)min((long long)CPB, op.ncells - c0);
+    for (int s = threadIdx.x; s < ncell; s += blockDim.x) load_geo<DIM>(op, c0 + s, geo[s]);
+    __syncthreads();
+    for (int t = threadIdx.x; t < ncell * op.nq; t += blockDim.x) {
+        int s = t / op.nq, q = t - s * op.nq;
+        const CellGeo<DIM> &G = geo[s];
+        double r[MAXOP];
+        if (op.nargs > 0) {
+            eval_args<DIM>(op, c0 + s, q, G, r); // standard kernel: result = input_args
+        } else {
+            double x[DIM];
+            eval_x<DIM>(G, op.qx + q * DIM, x);
+            const double *tab = op.tabulated ? op.tabulated + ((size_t)(c0 + s) * op.nq + q) * op.nout : nullptr;
+            lin_apply(op.kernel_id, x, op.params, r, op.nout, tab);
+        }
+        double sc = op.factor * op.qw[q] * G.vol;
+        for (int d = 0; d < op.nout; ++d) fq[(size_t)t * op.nout + d] = r[d] * sc;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < ncell * op.NR; e += blockDim.x) {
+        int s = e / op.NR, k = e - s * op.NR;
+        const CellGeo<DIM> &G = geo[s];
+        double acc = 0.0;
+        if (G.visited) {
+            for (int idt = 0; idt < op.ntest; ++idt) {
+                const ArgDev &ta = op.test[idt];
+                if (k < ta.locoff || k >= ta.locoff + ta.nd) continue;
+                int kk = k - ta.locoff;
+                for (int q = 0; q < op.nq; ++q) {
+                    CV ct = eval_cv<DIM>(ta, kk, q, G.Ainv, op.offdiag);
+                    const double *f = fq + ((size_t)s * op.nq + q) * op.nout;
+                    for (int t = 0; t < ct.len; ++t) acc += f[ta.opoff + ct.idx[t]] * ct.v[t];
+                }
+            }
+        }
+        bloc[(size_t)(c0 + s) * op.NR + k] = acc;
+    }
+}
+
+// =============================== NonlinearOperator =============================================
+template <int DIM>
+__global__ void __launch_bounds__(256)
+local_nonlinear_kernel(const __grid_constant__ OpDev op, double *__restrict__ loc, double *__restrict__ bloc, int CPB)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CellGeo<DIM> *geo = reinterpret_cast<CellGeo<DIM> *>(smem_raw);
+    const int nin = op.nin, nout = op.nout, JS = nin * nout;
+    double *jq = reinterpret_cast<double *>(geo + CPB); // [CPB][nq][nout*nin]
+    double *rq = jq + (size_t)CPB * op.nq * JS;         // [CPB][nq][nout]   (jac*u - value)*factor*w*vol
+    long long c0 = (long long)blockIdx.x * CPB;
+    int ncell = (int)min((long long)CPB, op.ncells - c0);
+    for (int s = threadIdx.x; s < ncell; s += blockDim.x) load_geo<DIM>(op, c0 + s, geo[s]);
+    __syncthreads();
+    for (int t = threadIdx.x; t < ncell * op.nq; t += blockDim.x) {
+        int s = t / op.nq, q = t - s * op.nq;
+        const CellGeo<DIM> &G = geo[s];
+        double u[MAXOP], val[MAXOP];
+        eval_args<DIM>(op, c0 + s, q, G, u);
+        double *J = jq + (size_t)t * JS;
+        nl_apply(op.kernel_id, DIM, u, op.params, val, J, nin, nout);
+        double sc = op.factor * op.qw[q] * G.vol;
+        for (int k = 0; k < nout; ++k) {
+            double sum = 0.0;
+            for (int d = 0; d < nin; ++d) sum += J[k * nin + d] * u[d];
+            rq[(size_t)t * nout + k] = (sum - val[k]) * sc;
+        }
+    }
+    __syncthreads();
+    const int NRC = op.NR * op.NC;
+    for (int e = threadIdx.x; e < ncell * NRC; e += blockDim.x) {
+        int s = e / NRC, r = e - s * NRC;
+        int j = r / op.NR, k = r - j * op.NR;
+        const CellGeo<DIM> &G = geo[s];
+        double acc = 0.0;
+        if (G.visited) {
+            for (int id = 0; id < op.nargs; ++id) {
+                const ArgDev &ga = op.args[id];
+                if (j < ga.locoff || j >= ga.locoff + ga.nd) continue;
+                int jj = j - ga.locoff;
+                for (int idt = 0; idt < op.ntest; ++idt) {
+                    const ArgDev &ta = op.test[idt];
+                    if (k < ta.locoff || k >= ta.locoff + ta.nd) continue;
+                    int kk = k - ta.locoff;
+                    double a = 0.0;
+                    for (int q = 0; q < op.nq; ++q) {
+                        CV cg = eval_cv<DIM>(ga, jj, q, G.Ainv, op.offdiag);
+                        CV ct = eval_cv<DIM>(ta, kk, q, G.Ainv, op.offdiag);
+                        const double *J = jq + ((size_t)s * op.nq + q) * JS;
+                        double w = op.qw[q];
+                        for (int t = 0; t < ct.len; ++t) {
+                            const double *Jrow = J + (ta.opoff + ct.idx[t]) * nin + ga.opoff;
+                            double tv = 0.0;
+                            for (int t2 = 0; t2 < cg.len; ++t2) tv += Jrow[cg.idx[t2]] * cg.v[t2];
+                            a += tv * ct.v[t] * w;
+                        }
+                    }
+                    acc += a * (op.factor * G.vol);
+                }
+            }
+        }
+        loc[(size_t)(c0 + s) * NRC + r] = acc;
+    }
+    for (int e = threadIdx.x; e < ncell * op.NR; e += blockDim.x) {
+        int s = e / op.NR, k = e - s * op.NR;
+        const CellGeo<DIM> &G = geo[s];
+        double acc = 0.0;
+        if (G.visited) {
+            for (int idt = 0; idt < op.ntest; ++idt) {
+                const ArgDev &ta = op.test[idt];
+                if (k < ta.locoff || k >= ta.locoff + ta.nd) continue;
+                int kk = k - ta.locoff;
+                for (int q = 0; q < op.nq; ++q) {
+                    CV ct = eval_cv<DIM>(ta, kk, q, G.Ainv, op.offdiag);
+                    const double *f = rq + ((size_t)s * op.nq + q) * nout;
+                    for (int t = 0; t < ct.len; ++t) acc += f[ta.opoff + ct.idx[t]] * ct.v[t];
+                }
+            }
+        }
+        bloc[(size_t)(c0 + s) * op.NR + k] = acc;
+    }
+}
+
+// x at quadrature points (extfem_quadrature_points)
+template <int DIM>
+__global__ void quadpoints_kernel(const __grid_constant__ OpDev op, double *__restrict__ xq)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= op.ncells * op.nq) return;
+    long long cell = t / op.nq;
+    int q = (int)(t - cell * op.nq);
+    CellGeo<DIM> G;
+    load_geo<DIM>(op, cell, G);
+    double x[DIM];
+    eval_x<DIM>(G, op.qx + q * DIM, x);
+    for (int d = 0; d < DIM; ++d) xq[t * DIM + d] = x[d];
+}
+
+} // namespace extfem

@@ -1,0 +1,269 @@
+"""ctypes binding of libextfem_cuda.so (include/extfem_cuda.h).
+
+This is the Python twin of the ``ccall`` stubs in julia/ExtFEMCuda.jl.  There is NO CPU
+fallback: if the shared library is missing or no CUDA device is present, loading / context
+creation raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libextfem_cuda.so")
+
+MAXARGS = 4
+OP_ID, OP_GRAD, OP_DIV, OP_SYMGRAD_VOIGT = 0, 1, 2, 3
+
+EXPORTS = [
+    "extfem_ctx_create", "extfem_ctx_destroy", "extfem_last_error", "extfem_kernel_id", "extfem_synchronize",
+    "extfem_launch_count", "extfem_last_timings", "extfem_mesh_set", "extfem_mesh_update_coords",
+    "extfem_space_set", "extfem_space_set_tables", "extfem_pattern_build", "extfem_pattern_dims",
+    "extfem_pattern_get", "extfem_assemble_bilinear", "extfem_assemble_linear", "extfem_assemble_nonlinear",
+    "extfem_quadrature_points", "extfem_values_get", "extfem_values_set", "extfem_device_ptrs",
+    "extfem_apply_penalties", "extfem_residual", "extfem_spmv", "extfem_cg",
+]
+
+
+class ExtFEMError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+class OpDesc(C.Structure):
+    _fields_ = [
+        ("ntest", C.c_int32), ("test_block", C.c_int32 * MAXARGS), ("test_op", C.c_int32 * MAXARGS),
+        ("nansatz", C.c_int32), ("ansatz_block", C.c_int32 * MAXARGS), ("ansatz_op", C.c_int32 * MAXARGS),
+        ("nargs", C.c_int32), ("args_block", C.c_int32 * MAXARGS), ("args_op", C.c_int32 * MAXARGS),
+        ("kernel_id", C.c_int32), ("nparams", C.c_int32), ("params", C.c_void_p),
+        ("factor", C.c_double), ("time", C.c_double), ("symgrad_offdiag", C.c_double),
+        ("quadorder", C.c_int32), ("bonus_quadorder", C.c_int32),
+        ("nregions", C.c_int32), ("regions", C.c_void_p),
+        ("transposed_copy", C.c_int32), ("lump", C.c_int32), ("coupling", C.c_void_p),
+        ("nq_custom", C.c_int32), ("qweights", C.c_void_p), ("qpoints", C.c_void_p), ("tabulated", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libextfem_cuda.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.extfem_last_error.restype = C.c_char_p
+        _lib.extfem_last_error.argtypes = [C.c_void_p]
+        _lib.extfem_launch_count.restype = C.c_int64
+        _lib.extfem_launch_count.argtypes = [C.c_void_p]
+        _lib.extfem_kernel_id.argtypes = [C.c_char_p]
+    return _lib
+
+
+def kernel_id(name: str) -> int:
+    kid = load_library().extfem_kernel_id(name.encode())
+    if kid < 0:
+        raise ExtFEMError(kid, load_library().extfem_last_error(None).decode())
+    return kid
+
+
+def _p(a):
+    """pointer of a numpy array / torch tensor / int address / None"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class Engine:
+    """One extfem context (one GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.lib.extfem_ctx_create(int(device), C.byref(self.ctx))
+        if rc != 0:
+            raise ExtFEMError(rc, self.lib.extfem_last_error(None).decode())
+        self._keep = []
+
+    def close(self):
+        if self.ctx:
+            self.lib.extfem_ctx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ExtFEMError(rc, self.lib.extfem_last_error(self.ctx).decode())
+
+    # ---- grid / spaces / pattern ------------------------------------------------------------
+    def mesh_set(self, coords, cellnodes, cellregions=None, cellvolumes=None) -> int:
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        cellnodes = np.ascontiguousarray(cellnodes)
+        assert cellnodes.dtype in (np.int32, np.int64)
+        reg = None if cellregions is None else np.ascontiguousarray(cellregions, dtype=np.int32)
+        vol = None if cellvolumes is None else np.ascontiguousarray(cellvolumes, dtype=np.float64)
+        out = C.c_int()
+        self._check(self.lib.extfem_mesh_set(self.ctx, coords.shape[1], C.c_int64(cellnodes.shape[0]),
+                                             C.c_int64(coords.shape[0]), _p(coords), _p(cellnodes),
+                                             cellnodes.dtype.itemsize, _p(reg), _p(vol), C.byref(out)))
+        return out.value
+
+    def mesh_update_coords(self, mesh: int, coords, cellvolumes=None):
+        self._check(self.lib.extfem_mesh_update_coords(self.ctx, mesh, _p(coords), _p(cellvolumes)))
+
+    def space_set(self, mesh: int, fetype: int, ncomp: int, celldofs, ndofs: int) -> int:
+        celldofs = np.ascontiguousarray(celldofs)
+        assert celldofs.dtype in (np.int32, np.int64)
+        out = C.c_int()
+        self._check(self.lib.extfem_space_set(self.ctx, mesh, fetype, ncomp, _p(celldofs), celldofs.dtype.itemsize,
+                                              celldofs.shape[1], C.c_int64(ndofs), C.byref(out)))
+        return out.value
+
+    def pattern_build(self, rowspaces, colspaces=None, block_coupling=None) -> int:
+        colspaces = rowspaces if colspaces is None else colspaces
+        rs = (C.c_int * len(rowspaces))(*rowspaces)
+        cs = (C.c_int * len(colspaces))(*colspaces)
+        bc = None if block_coupling is None else np.ascontiguousarray(block_coupling, dtype=np.uint8)
+        out = C.c_int()
+        self._check(self.lib.extfem_pattern_build(self.ctx, len(rowspaces), rs, len(colspaces), cs, _p(bc), C.byref(out)))
+        return out.value
+
+    def pattern_dims(self, pattern: int):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.extfem_pattern_dims(self.ctx, pattern, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def pattern_get(self, pattern: int):
+        nrows, ncols, nnz = self.pattern_dims(pattern)
+        colptr = np.empty(ncols + 1, np.int64)
+        rowval = np.empty(nnz, np.int64)
+        self._check(self.lib.extfem_pattern_get(self.ctx, pattern, _p(colptr), _p(rowval)))
+        return colptr, rowval
+
+    # ---- operators -------------------------------------------------------------------------------
+    def make_opdesc(self, test, ansatz=(), args=(), kernel_id=1, params=(), factor=1.0, time=0.0, quadorder=-1,
+                    bonus_quadorder=0, regions=(), transposed_copy=0, lump=0, coupling=None, offdiag=1.0,
+                    qweights=None, qpoints=None, tabulated=None):
+        """test/ansatz/args: sequences of (block, op)."""
+        d = OpDesc()
+        keep = []
+        for name, lst in (("test", test), ("ansatz", ansatz), ("args", args)):
+            setattr(d, "n" + name, len(lst))
+            for i, (blk, op) in enumerate(lst):
+                getattr(d, name + "_block")[i] = blk
+                getattr(d, name + "_op")[i] = op
+        d.kernel_id = kernel_id
+        p = np.ascontiguousarray(np.asarray(params, dtype=np.float64).ravel())
+        r = np.ascontiguousarray(np.asarray(regions, dtype=np.int32).ravel())
+        keep += [p, r]
+        d.nparams, d.params = p.size, _p(p)
+        d.factor, d.time, d.symgrad_offdiag = float(factor), float(time), float(offdiag)
+        d.quadorder, d.bonus_quadorder = int(quadorder), int(bonus_quadorder)
+        d.nregions, d.regions = r.size, _p(r)
+        d.transposed_copy, d.lump = int(transposed_copy), int(lump)
+        if coupling is not None:
+            cp = np.ascontiguousarray(coupling, dtype=np.uint8)
+            keep.append(cp)
+            d.coupling = _p(cp)
+        if qweights is not None:
+            qw = np.ascontiguousarray(qweights, dtype=np.float64)
+            qx = np.ascontiguousarray(qpoints, dtype=np.float64)
+            keep += [qw, qx]
+            d.nq_custom, d.qweights, d.qpoints = qw.size, _p(qw), _p(qx)
+        if tabulated is not None:
+            if isinstance(tabulated, np.ndarray):
+                tabulated = np.ascontiguousarray(tabulated, dtype=np.float64)
+            keep.append(tabulated)
+            d.tabulated = _p(tabulated)
+        d._keep = keep
+        return d
+
+    def assemble_bilinear(self, pattern, desc, sol=None, accumulate=False, nzval_out=None):
+        self._check(self.lib.extfem_assemble_bilinear(self.ctx, pattern, C.byref(desc), _p(sol), int(accumulate), _p(nzval_out)))
+
+    def assemble_linear(self, pattern, desc, sol=None, accumulate=False, b_out=None):
+        self._check(self.lib.extfem_assemble_linear(self.ctx, pattern, C.byref(desc), _p(sol), int(accumulate), _p(b_out)))
+
+    def assemble_nonlinear(self, pattern, desc, sol, accumulate=False, nzval_out=None, b_out=None):
+        self._check(self.lib.extfem_assemble_nonlinear(self.ctx, pattern, C.byref(desc), _p(sol), int(accumulate),
+                                                       _p(nzval_out), _p(b_out)))
+
+    def quadrature_points(self, pattern, desc, is_linear=True):
+        nq = C.c_int()
+        self._check(self.lib.extfem_quadrature_points(self.ctx, pattern, C.byref(desc), int(is_linear), C.byref(nq), None))
+        return nq.value
+
+    def quadrature_points_x(self, pattern, desc, ncells, dim, is_linear=True):
+        nq = self.quadrature_points(pattern, desc, is_linear)
+        xq = np.empty((ncells, nq, dim))
+        self._check(self.lib.extfem_quadrature_points(self.ctx, pattern, C.byref(desc), int(is_linear), C.byref(C.c_int()), _p(xq)))
+        return xq
+
+    # ---- device-resident system ----------------------------------------------------------------
+    def values_get(self, pattern, want_nzval=True, want_b=True):
+        nrows, ncols, nnz = self.pattern_dims(pattern)
+        nz = np.empty(nnz) if want_nzval else None
+        b = np.empty(nrows) if want_b else None
+        self._check(self.lib.extfem_values_get(self.ctx, pattern, _p(nz), _p(b)))
+        return nz, b
+
+    def values_set(self, pattern, nzval=None, b=None):
+        self._check(self.lib.extfem_values_set(self.ctx, pattern, _p(nzval), _p(b)))
+
+    def device_ptrs(self, pattern):
+        ptrs = [C.c_void_p() for _ in range(4)]
+        self._check(self.lib.extfem_device_ptrs(self.ctx, pattern, *[C.byref(p) for p in ptrs]))
+        return [p.value for p in ptrs]
+
+    def apply_penalties(self, pattern, dofs, values=None, penalty=1e30):
+        dofs = np.ascontiguousarray(dofs, dtype=np.int64)
+        vals = None if values is None else np.ascontiguousarray(values, dtype=np.float64)
+        self._check(self.lib.extfem_apply_penalties(self.ctx, pattern, C.c_int64(dofs.size), _p(dofs), _p(vals), C.c_double(penalty)))
+
+    def residual(self, pattern, sol):
+        nrows, _, _ = self.pattern_dims(pattern)
+        sol = np.ascontiguousarray(sol, dtype=np.float64)
+        res = np.empty(nrows)
+        self._check(self.lib.extfem_residual(self.ctx, pattern, _p(sol), _p(res)))
+        return res
+
+    def spmv(self, pattern, x):
+        nrows, _, _ = self.pattern_dims(pattern)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(nrows)
+        self._check(self.lib.extfem_spmv(self.ctx, pattern, _p(x), _p(y)))
+        return y
+
+    def cg(self, pattern, b=None, x0=None, rtol=1e-10, maxit=10000):
+        nrows, _, _ = self.pattern_dims(pattern)
+        x = np.zeros(nrows) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        it, rr = C.c_int(), C.c_double()
+        self._check(self.lib.extfem_cg(self.ctx, pattern, _p(bb), _p(x), C.c_double(rtol), int(maxit), C.byref(it), C.byref(rr)))
+        return x, it.value, rr.value
+
+    def synchronize(self):
+        self._check(self.lib.extfem_synchronize(self.ctx))
+
+    def launch_count(self) -> int:
+        return int(self.lib.extfem_launch_count(self.ctx))
+
+    def last_timings(self):
+        ms = (C.c_double * 3)()
+        self._check(self.lib.extfem_last_timings(self.ctx, ms))
+        return list(ms)

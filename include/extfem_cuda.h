@@ -1,0 +1,185 @@
+/*
+ * extfem_cuda.h -- C-ABI of libextfem_cuda.so, the B200 (sm_100a) assembly engine behind
+ * ExtendableFEM.jl's operator API.
+ *
+ * The reference has no FFI: its hot path sits behind Julia multiple dispatch.  The seam this
+ * library replaces is the closure `O.assembler` that `build_assembler!` creates and
+ * `assemble!` invokes with raw arrays:
+ *
+ *   BilinearOperator   src/common_operators/bilinear_operator.jl:659 (build_assembler!),
+ *                      :820-951 / :451-596 (assembly_loop), :955-1003 (assembler), :1013/:1050 (assemble!)
+ *   LinearOperator     src/common_operators/linear_operator.jl:482 / :241 (build_assembler!),
+ *                      :584-640 / :359-438 (assembly_loop), :697/:774 (assemble!)
+ *   NonlinearOperator  src/common_operators/nonlinear_operator.jl:129 (build_assembler!),
+ *                      :283-436 (assembly_loop), :479/:510 (assemble!)
+ *   assemble_system!   src/solvers.jl:124-195 (zeroing, flush!), residual src/solvers.jl:38-43
+ *
+ * Conventions
+ *  - every function returns EXTFEM_OK (0) or a negative EXTFEM_ERR_* code; the message is
+ *    available from extfem_last_error(ctx).  No C++ exception crosses the boundary.
+ *  - index arrays handed in are 1-based (Julia), 4 or 8 bytes wide (`index_bytes`), laid out
+ *    exactly like the Julia arrays: coords[dim, nnodes], cellnodes[dim+1, ncells],
+ *    celldofs[ndofs4cell, ncells] column-major (== C row-major [nitems][k]).
+ *  - host arrays are borrowed for the duration of the call only.  Every data pointer may be a
+ *    host pointer OR a device pointer (unified addressing; copies use cudaMemcpyDefault), so a
+ *    caller that already has device-resident data (CUDA.jl, torch) pays no PCIe transfer.
+ *  - the matrix is CSC, Int64, 1-based, rows sorted per column -- the layout of
+ *    `A.entries.cscmatrix` (src/solver_config.jl:190, src/solvers.jl:134).  The CSR arrays
+ *    north_star mentions are the same arrays for the transposed matrix.
+ *  - the sparsity pattern is STRUCTURAL (dofs sharing a cell, filtered by the block coupling);
+ *    the reference's value-dependent pattern (entries exactly 0.0 are never inserted,
+ *    bilinear_operator.jl:925) is always a subset of it.
+ *  - a context is not re-entrant; calls on one context are serialised by the caller.
+ *  - there is no CPU fallback: without a CUDA device extfem_ctx_create fails.
+ */
+#ifndef EXTFEM_CUDA_H
+#define EXTFEM_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct extfem_ctx extfem_ctx;
+
+/* ---- error codes ----------------------------------------------------------------------- */
+enum {
+    EXTFEM_OK = 0,
+    EXTFEM_ERR_UNREGISTERED_KERNEL = -1, /* Julia closure has no registry entry (north_star)   */
+    EXTFEM_ERR_UNSUPPORTED_ELEMENT = -2, /* fetype / operator / entity outside the hot path     */
+    EXTFEM_ERR_BAD_ARGUMENT = -3,
+    EXTFEM_ERR_CUDA = -4,
+    EXTFEM_ERR_NCCL = -5,
+    EXTFEM_ERR_CAPACITY = -6             /* an internal fixed capacity was exceeded             */
+};
+
+/* ---- finite elements / function operators ----------------------------------------------- */
+enum { EXTFEM_FE_H1P1 = 1, EXTFEM_FE_H1P2 = 2, EXTFEM_FE_TABULATED = 100 };
+/* function operators (ExtendableFEMBase: Identity, Gradient, Divergence, SymmetricGradient) */
+enum { EXTFEM_OP_ID = 0, EXTFEM_OP_GRAD = 1, EXTFEM_OP_DIV = 2, EXTFEM_OP_SYMGRAD_VOIGT = 3 };
+
+/* ---- kernel registry; extfem_kernel_id("name") resolves names ------ */
+enum { /* BilinearOperator kernels: result = C(x, args) * input */
+    EXTFEM_BLK_STANDARD = 1,     /* "standard"      ExtendableFEMBase.standard_kernel (bilinear_operator.jl:248) */
+    EXTFEM_BLK_DCR = 2,          /* "dcr"           Example220:66-72; params alpha, nu, beta[dim]                */
+    EXTFEM_BLK_STOKES = 3,       /* "stokes"        docs/src/bilinearoperator.md:37-45; params mu                */
+    EXTFEM_BLK_LINNSE7 = 4,      /* "linnse7"       test/test_nonlinear_operator.jl:18-28; params mu, alpha      */
+    EXTFEM_BLK_HOOKE_GRAD = 5,   /* "hooke_grad"    isotropic Hooke on grad(u); params mu, lambda                */
+    EXTFEM_BLK_HOOKE_VOIGT = 6,  /* "hooke_voigt"   Example312:55 sigma = C*epsV(u); params C row-major          */
+    EXTFEM_BLK_CONVECT_ARGS = 7  /* "convect_args"  (args . grad) u, kernel with args (bilinear_operator.jl:536)  */
+};
+enum { /* LinearOperator kernels f(x) */
+    EXTFEM_LIN_CONSTANT_ONE = 1,    /* "constant_one"    constant_one_kernel (linear_operator.jl:159)  */
+    EXTFEM_LIN_CONSTANT_PARAMS = 2, /* "constant_params" result .= params (Example330:44, Example312:58) */
+    EXTFEM_LIN_XY = 3,              /* "xy"              README.md:37-40 / Example201:32-35              */
+    EXTFEM_LIN_SINCOS301 = 4,       /* "sincos301"       Example301:33-35; params mu                     */
+    EXTFEM_LIN_TABULATED = 5        /* "tabulated"       any Julia closure, evaluated by the host at the
+                                                         quadrature points (extfem_quadrature_points)    */
+};
+enum { /* NonlinearOperator kernels with analytic Jacobians */
+    EXTFEM_NL_NSE2D = 1,       /* "nse2d"       Example250:59-74; params mu          */
+    EXTFEM_NL_LINNSE7 = 2,     /* "nl_linnse7"  test/test_nonlinear_operator.jl:18-28 */
+    EXTFEM_NL_NEOHOOKE3D = 3,  /* "neohooke3d"  Example330:49-57 (DW); params mu, lambda */
+    EXTFEM_NL_RCD = 4          /* "rcd"         Example108:40-45                        */
+};
+
+#define EXTFEM_MAXARGS 4 /* (unknown, operator) pairs per role */
+
+/* One operator, flattened from the Julia kwargs tables (bilinear_operator.jl:56-73,
+ * linear_operator.jl:34-47, nonlinear_operator.jl:31-48).  `*_block` index the row (test) /
+ * column (ansatz, args) blocks of the pattern, like `A[j,j]` in bilinear_operator.jl:1030. */
+typedef struct {
+    int32_t ntest, test_block[EXTFEM_MAXARGS], test_op[EXTFEM_MAXARGS];
+    int32_t nansatz, ansatz_block[EXTFEM_MAXARGS], ansatz_op[EXTFEM_MAXARGS];
+    int32_t nargs, args_block[EXTFEM_MAXARGS], args_op[EXTFEM_MAXARGS];
+    int32_t kernel_id;
+    int32_t nparams;
+    const double *params;      /* qpinfo.params                                        */
+    double factor;             /* :factor                                              */
+    double time;               /* qpinfo.time                                          */
+    double symgrad_offdiag;    /* offdiagval of SymmetricGradient operators            */
+    int32_t quadorder;         /* :quadorder, -1 == "auto"                             */
+    int32_t bonus_quadorder;   /* :bonus_quadorder                                     */
+    int32_t nregions;          /* :regions ([] == all)                                 */
+    const int32_t *regions;
+    int32_t transposed_copy;   /* :transposed_copy (0, 1, -1)                          */
+    int32_t lump;              /* :lump (0, 1, 2)                                      */
+    const uint8_t *coupling;   /* [nansatz][ntest] couples_with (NULL == all couple)   */
+    /* optional host-supplied quadrature rule (from ExtendableFEMBase's QuadratureRule) */
+    int32_t nq_custom;
+    const double *qweights;    /* [nq]                                                 */
+    const double *qpoints;     /* [nq][dim]                                            */
+    const double *tabulated;   /* EXTFEM_LIN_TABULATED: [ncells][nq][oplen]            */
+} extfem_opdesc;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int extfem_ctx_create(int device, extfem_ctx **out);
+int extfem_ctx_destroy(extfem_ctx *ctx);
+const char *extfem_last_error(extfem_ctx *ctx);      /* ctx may be NULL: last global error    */
+int extfem_kernel_id(const char *name);              /* <0: EXTFEM_ERR_UNREGISTERED_KERNEL     */
+int extfem_synchronize(extfem_ctx *ctx);
+/* number of kernel launches issued by this context since creation (bench "gpu_launches") */
+int64_t extfem_launch_count(extfem_ctx *ctx);
+/* device time in ms of the phases of the last assemble call (CUDA events):
+ * [0] local (cell) kernel, [1] gather kernel(s), [2] total incl. copies.  */
+int extfem_last_timings(extfem_ctx *ctx, double *ms3);
+
+/* ---- grid:  xgrid[Coordinates], xgrid[CellNodes], xgrid[CellRegions], xgrid[CellVolumes]
+ *      (bilinear_operator.jl:693-695) ------------------------------------------------------- */
+int extfem_mesh_set(extfem_ctx *ctx, int dim, int64_t ncells, int64_t nnodes, const double *coords,
+                    const void *cellnodes, int index_bytes, const int32_t *cellregions /* NULL: all 1 */,
+                    const double *cellvolumes /* NULL: computed */, int *mesh_out);
+/* new node coordinates for an existing mesh (moving meshes; refreshes the geometry cache) */
+int extfem_mesh_update_coords(extfem_ctx *ctx, int mesh, const double *coords, const double *cellvolumes);
+
+/* ---- FESpace: FES[CellDofs] via get_dofmap (src/helper_functions.jl:561-567) ------------- */
+int extfem_space_set(extfem_ctx *ctx, int mesh, int fetype, int ncomp, const void *celldofs, int index_bytes,
+                     int ndofs4cell, int64_t ndofs, int *space_out);
+/* EXTFEM_FE_TABULATED: reference basis supplied by the host (any affine H1 Lagrange-type element):
+ * the engine evaluates vals/grads through callbacks-free tables given per quadrature rule.     */
+int extfem_space_set_tables(extfem_ctx *ctx, int space, int nq, int nscalar, const double *refvals /*[nq][nscalar]*/,
+                            const double *refgrads /*[nq][nscalar][dim]*/);
+
+/* ---- FEMatrix pattern (replaces ExtendableSparse rawupdateindex!/flush!) ------------------
+ * Block system with row blocks `rowspaces` and column blocks `colspaces`; block (r,c) is
+ * present when block_coupling[c*nrow + r] != 0 (NULL: all).                                   */
+int extfem_pattern_build(extfem_ctx *ctx, int nrowspaces, const int *rowspaces, int ncolspaces, const int *colspaces,
+                         const uint8_t *block_coupling, int *pattern_out);
+int extfem_pattern_dims(extfem_ctx *ctx, int pattern, int64_t *nrows, int64_t *ncols, int64_t *nnz);
+int extfem_pattern_get(extfem_ctx *ctx, int pattern, int64_t *colptr /*[ncols+1]*/, int64_t *rowval /*[nnz]*/);
+
+/* ---- assembly.  accumulate == 0 first zeroes the device values (fill!(nzval,0),
+ *      src/solvers.jl:130-135); out pointers may be NULL (values stay device-resident).      */
+int extfem_assemble_bilinear(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, const double *sol /* args */,
+                             int accumulate, double *nzval_out);
+int extfem_assemble_linear(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, const double *sol /* args */,
+                           int accumulate, double *b_out);
+int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, const double *sol,
+                              int accumulate, double *nzval_out, double *b_out);
+/* x at the quadrature points the operator will use: xq[ncells][nq][dim]; *nq_out = nq.
+ * xq may be NULL to query nq only.  (Host evaluates its closure there -> EXTFEM_LIN_TABULATED.) */
+int extfem_quadrature_points(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, int is_linear, int *nq_out,
+                             double *xq);
+
+/* ---- device-resident system --------------------------------------------------------------- */
+int extfem_values_get(extfem_ctx *ctx, int pattern, double *nzval /*NULL ok*/, double *b /*NULL ok*/);
+int extfem_values_set(extfem_ctx *ctx, int pattern, const double *nzval /*NULL ok*/, const double *b /*NULL ok*/);
+/* raw device pointers (colptr int64 0-based, rowval int32 0-based, nzval, b) for zero-copy users */
+int extfem_device_ptrs(extfem_ctx *ctx, int pattern, void **colptr, void **rowval, void **nzval, void **b);
+/* apply_penalties! (homogeneousdata_operator.jl:186-201): A[d,d] = penalty, b[d] = penalty*value[d] */
+int extfem_apply_penalties(extfem_ctx *ctx, int pattern, int64_t ndofs, const int64_t *dofs /*1-based*/,
+                           const double *values /*NULL: 0*/, double penalty);
+/* compute_nonlinear_residual! (src/solvers.jl:38-43): res = b - A*sol */
+int extfem_residual(extfem_ctx *ctx, int pattern, const double *sol, double *res_out);
+/* y = A*x on the device-resident matrix */
+int extfem_spmv(extfem_ctx *ctx, int pattern, const double *x, double *y);
+/* Jacobi-preconditioned CG on the device-resident system (square patterns); b == NULL uses the
+ * device-resident right-hand side.  x is in/out (initial guess).                              */
+int extfem_cg(extfem_ctx *ctx, int pattern, const double *b, double *x, double rtol, int maxit, int *iters,
+              double *relres);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXTFEM_CUDA_H */
