@@ -39,7 +39,15 @@ struct Space {
     DevBuf tab_vals, tab_grads;
 };
 
+struct FastPlan {
+    bool ready = false;
+    int nchunks = 0;
+    DevBuf chunkptr, slotcol, warpniter, warpoff, rec;
+};
+
 struct Pattern {
+    std::vector<std::unique_ptr<FastPlan>> fastplans; // per column block (diagonal blocks only)
+    std::vector<long long> hcolptr;                   // host copy of colptr (plan construction)
     std::vector<int> rowspaces, colspaces;
     std::vector<long long> rowoff, coloff;     // size n+1
     std::vector<int> rowlocoff;                // per row block: offset in the posmap row
@@ -80,9 +88,11 @@ struct Ctx {
     std::map<TableKey, std::unique_ptr<DevTables>> tables;
     std::map<std::pair<int, int>, std::unique_ptr<DevQuad>> quads; // (dim, order)
     DevBuf custom_qw, custom_qx;
-    DevBuf loc, bloc, sol, params_scratch, tab;
+    DevBuf loc, bloc, sol, params_scratch, tab, geo, visit;
+    bool fast_enabled = true;
     long long launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t uev[16] = {};
     double last_ms[3] = {0, 0, 0};
 };
 
@@ -492,10 +502,156 @@ static int finish_timing(Ctx *ctx)
     return 0;
 }
 
+// ---- fast path (fastpath.cuh) --------------------------------------------------------------------
+static int build_fast_plan(Ctx *ctx, Pattern &P, int b, int ns)
+{
+    if (!P.fastplans[b]) P.fastplans[b] = std::make_unique<FastPlan>();
+    FastPlan &F = *P.fastplans[b];
+    if (F.ready) return 0;
+    Space &S = *ctx->spaces[P.colspaces[b]];
+    Mesh &M = *ctx->meshes[S.mesh];
+    const long long c0 = P.coloff[b], c1 = P.coloff[b + 1];
+    // chunks in block-local column indices
+    std::vector<int> chunks;
+    chunks.push_back(0);
+    long long k = c0;
+    while (k < c1) {
+        long long k2 = k, base = P.hcolptr[k];
+        while (k2 < c1 && k2 - k < FP_THREADS && P.hcolptr[k2 + 1] - base <= FP_MAXNNZ) ++k2;
+        if (k2 == k) return fail(ctx, EXTFEM_ERR_CAPACITY, "matrix column too long for the fast gather kernel");
+        chunks.push_back((int)(k2 - c0));
+        k = k2;
+    }
+    F.nchunks = (int)chunks.size() - 1;
+    if (int rc = upload(ctx, F.chunkptr, chunks.data(), chunks.size() * 4)) return rc;
+    DevBuf sig;
+    if (int rc = ensure(ctx, sig, (size_t)S.ndofs * 8)) return rc;
+    fp_signature_kernel<<<nblocks(S.ndofs, 256), 256, 0, ctx->stream>>>(S.ndofs, S.adjptr.as<long long>(), S.adjloc.as<unsigned char>(),
+                                                                       sig.as<unsigned long long>());
+    LAUNCHED(ctx);
+    if (int rc = ensure(ctx, F.slotcol, (size_t)F.nchunks * FP_THREADS * 4)) return rc;
+    if (int rc = ensure(ctx, F.warpniter, (size_t)F.nchunks * FP_WARPS * 4)) return rc;
+    fp_sort_kernel<<<F.nchunks, 512, 0, ctx->stream>>>(F.chunkptr.as<int>(), sig.as<unsigned long long>(), S.adjptr.as<long long>(),
+                                                      F.slotcol.as<int>(), F.warpniter.as<int>());
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+    std::vector<int> hn((size_t)F.nchunks * FP_WARPS);
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(hn.data(), F.warpniter.p, hn.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const int rw = fp_rw(ns);
+    std::vector<long long> hoff(hn.size());
+    long long tot = 0;
+    for (size_t i = 0; i < hn.size(); ++i) { hoff[i] = tot; tot += (long long)hn[i] * rw * 32; }
+    if (int rc = upload(ctx, F.warpoff, hoff.data(), hoff.size() * 8)) return rc;
+    if (int rc = ensure(ctx, F.rec, (size_t)tot * 4)) return rc;
+    long long nslots = (long long)F.nchunks * FP_THREADS;
+    fp_fill_kernel<unsigned char><<<nblocks(nslots, 256), 256, 0, ctx->stream>>>(
+        nslots, ns, rw, P.NRpat, F.slotcol.as<int>(), F.warpniter.as<int>(), F.warpoff.as<long long>(), S.adjptr.as<long long>(),
+        S.adjcell.as<int>(), S.adjloc.as<unsigned char>(), P.posmap[b]->as<unsigned char>() + P.rowlocoff[b], F.rec.as<unsigned>());
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    (void)M;
+    F.ready = true;
+    return 0;
+}
+
+template <int DIM, int NS, int FORM>
+static int launch_fast(Ctx *ctx, Pattern &P, FastPlan &F, int b, const Prepared &R, const extfem_opdesc *d, int accumulate)
+{
+    constexpr int NG = fp_ng(DIM, FORM);
+    Mesh &M = *R.mesh;
+    if (int rc = ensure(ctx, ctx->geo, (size_t)M.ncells * NG * 8)) return rc;
+    if (d->nregions > 0) if (int rc = upload(ctx, ctx->visit, d->regions, (size_t)d->nregions * 4)) return rc;
+    fp_geo_kernel<DIM, FORM><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(
+        M.ncells, M.coords.as<double>(), M.cellnodes.as<int>(), M.regions.as<int>(), M.vol.as<double>(), d->factor, d->nregions,
+        ctx->visit.as<int>(), ctx->geo.as<double>());
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    FastArgs A;
+    A.plan.nchunks = F.nchunks; A.plan.chunkptr = F.chunkptr.as<int>(); A.plan.slotcol = F.slotcol.as<int>();
+    A.plan.warpniter = F.warpniter.as<int>(); A.plan.warpoff = F.warpoff.as<long long>(); A.plan.rec = F.rec.as<unsigned>();
+    A.colptr = P.colptr.as<long long>() + P.coloff[b];
+    A.nzval = P.nzval.as<double>(); A.geo = ctx->geo.as<double>(); A.overwrite = !accumulate;
+    static bool attr_set = false;
+    auto kern = fp_gather_kernel<NS, NG>;
+    if (!attr_set) {
+        EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_DOUBLES * 8));
+        attr_set = true;
+    }
+    kern<<<F.nchunks, FP_THREADS, FP_SMEM_DOUBLES * 8, ctx->stream>>>(A);
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+    EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    return 0;
+}
+
 // fast paths for the headline configurations; *fast == false -> generic path
-static int try_fast_bilinear(Ctx *, Pattern &, const Prepared &, const extfem_opdesc *, int, bool *fast)
+static int try_fast_bilinear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem_opdesc *d, int accumulate, bool *fast)
 {
     *fast = false;
+    if (!ctx->fast_enabled) return 0;
+    const OpDev &op = R.op;
+    if (d->kernel_id != EXTFEM_BLK_STANDARD || d->ntest != 1 || d->nansatz != 1 || d->nargs != 0 || d->lump != 0 ||
+        d->transposed_copy != 0 || d->test_block[0] != d->ansatz_block[0])
+        return 0;
+    const int b = d->test_block[0];
+    if (b >= (int)P.colspaces.size() || b >= (int)P.rowspaces.size() || P.rowspaces[b] != P.colspaces[b]) return 0;
+    if (!P.coupling[(size_t)b * P.rowspaces.size() + b] || P.poswidth != 1) return 0;
+    Space &S = *ctx->spaces[P.colspaces[b]];
+    if (S.ncomp != 1 || S.nscalar > 10) return 0;
+    int form;
+    if (d->test_op[0] == EXTFEM_OP_GRAD && d->ansatz_op[0] == EXTFEM_OP_GRAD) form = FP_FORM_LAPLACE;
+    else if (d->test_op[0] == EXTFEM_OP_ID && d->ansatz_op[0] == EXTFEM_OP_ID) form = FP_FORM_MASS;
+    else return 0;
+    // other column blocks of the pattern are not touched by this operator: zero them when overwriting
+    if (!accumulate && P.colspaces.size() > 1) {
+        for (size_t c = 0; c < P.colspaces.size(); ++c) {
+            if ((int)c == b) continue;
+            long long n0 = P.hcolptr[P.coloff[c]], n1 = P.hcolptr[P.coloff[c + 1]];
+            EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(P.nzval.as<double>() + n0, 0, (size_t)(n1 - n0) * 8, ctx->stream));
+        }
+    }
+    const int dim = op.dim, ns = S.nscalar;
+    if (int rc = build_fast_plan(ctx, P, b, ns)) return rc;
+    // reference tables S[g][t][kl] from the SAME quadrature rule / basis as the generic path
+    {
+        QuadRule Q;
+        Q.dim = dim; Q.nq = op.nq;
+        Q.w.resize(op.nq); Q.x.resize((size_t)op.nq * dim);
+        EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.w.data(), op.qw, op.nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.x.data(), op.qx, (size_t)op.nq * dim * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<double> v, g;
+        ref_basis(S.order, dim, Q, v, g);
+        const int ng = fp_ng(dim, form);
+        std::vector<double> T((size_t)ng * ns * ns, 0.0);
+        for (int q = 0; q < Q.nq; ++q)
+            for (int t = 0; t < ns; ++t)
+                for (int kl = 0; kl < ns; ++kl) {
+                    if (form == FP_FORM_MASS) { T[(size_t)t * ns + kl] += Q.w[q] * v[(size_t)q * ns + t] * v[(size_t)q * ns + kl]; continue; }
+                    int gi = 0;
+                    for (int dd = 0; dd < dim; ++dd)
+                        for (int ee = dd; ee < dim; ++ee, ++gi) {
+                            double a = g[((size_t)q * ns + t) * dim + dd] * g[((size_t)q * ns + kl) * dim + ee];
+                            if (ee != dd) a += g[((size_t)q * ns + t) * dim + ee] * g[((size_t)q * ns + kl) * dim + dd];
+                            T[((size_t)gi * ns + t) * ns + kl] += Q.w[q] * a;
+                        }
+                }
+        EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_fp_S, T.data(), T.size() * 8, 0, cudaMemcpyHostToDevice, ctx->stream));
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    FastPlan &F = *P.fastplans[b];
+    int rc = -1;
+#define FP_CASE(D, N, FRM) if (dim == D && ns == N && form == FRM) rc = launch_fast<D, N, FRM>(ctx, P, F, b, R, d, accumulate);
+    FP_CASE(1, 2, FP_FORM_LAPLACE) FP_CASE(1, 3, FP_FORM_LAPLACE) FP_CASE(2, 3, FP_FORM_LAPLACE) FP_CASE(2, 6, FP_FORM_LAPLACE)
+    FP_CASE(3, 4, FP_FORM_LAPLACE) FP_CASE(3, 10, FP_FORM_LAPLACE)
+    FP_CASE(1, 2, FP_FORM_MASS) FP_CASE(1, 3, FP_FORM_MASS) FP_CASE(2, 3, FP_FORM_MASS) FP_CASE(2, 6, FP_FORM_MASS)
+    FP_CASE(3, 4, FP_FORM_MASS) FP_CASE(3, 10, FP_FORM_MASS)
+#undef FP_CASE
+    if (rc == -1) return 0; // no instantiation: generic path
+    if (rc) return rc;
+    *fast = true;
     return 0;
 }
 
@@ -531,6 +687,8 @@ int extfem_ctx_create(int device, extfem_ctx **out)
         return fail(nullptr, EXTFEM_ERR_CUDA, "cannot initialise device");
     }
     for (auto &ev : C->ev) cudaEventCreate(&ev);
+    for (auto &ev : C->uev) cudaEventCreate(&ev);
+    if (const char *e = getenv("EXTFEM_DISABLE_FASTPATH")) C->fast_enabled = !(e[0] == '1');
     *out = reinterpret_cast<extfem_ctx *>(C);
     return EXTFEM_OK;
 }
@@ -542,6 +700,7 @@ int extfem_ctx_destroy(extfem_ctx *ctx)
     cudaSetDevice(C->device);
     cudaStreamSynchronize(C->stream);
     for (auto &ev : C->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : C->uev) if (ev) cudaEventDestroy(ev);
     C->patterns.clear(); C->spaces.clear(); C->meshes.clear();
     cudaStream_t s = C->stream;
     delete C;
@@ -577,12 +736,38 @@ int extfem_synchronize(extfem_ctx *ctx)
     return EXTFEM_OK;
 }
 
+int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
+{
+    CTX_GUARD(ctx);
+    if (key && !strcmp(key, "fastpath")) { C->fast_enabled = value != 0; return EXTFEM_OK; }
+    return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("unknown option ") + (key ? key : "(null)"));
+}
+
 int64_t extfem_launch_count(extfem_ctx *ctx) { return ctx ? reinterpret_cast<Ctx *>(ctx)->launches : 0; }
 
 int extfem_last_timings(extfem_ctx *ctx, double *ms3)
 {
     CTX_GUARD(ctx);
     for (int i = 0; i < 3; ++i) ms3[i] = C->last_ms[i];
+    return EXTFEM_OK;
+}
+
+int extfem_event_record(extfem_ctx *ctx, int slot)
+{
+    CTX_GUARD(ctx);
+    if (slot < 0 || slot >= 16) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "event slot out of range");
+    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->uev[slot], C->stream));
+    return EXTFEM_OK;
+}
+
+int extfem_event_elapsed_ms(extfem_ctx *ctx, int a, int b, double *ms)
+{
+    CTX_GUARD(ctx);
+    if (a < 0 || a >= 16 || b < 0 || b >= 16 || !ms) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "event slot out of range");
+    EXTFEM_CUDA_CHECK(C, cudaEventSynchronize(C->uev[b]));
+    float f = 0;
+    EXTFEM_CUDA_CHECK(C, cudaEventElapsedTime(&f, C->uev[a], C->uev[b]));
+    *ms = f;
     return EXTFEM_OK;
 }
 
@@ -786,6 +971,8 @@ int extfem_pattern_build(extfem_ctx *ctx, int nrow, const int *rowspaces, int nc
         }
     }
     P.nchunks = (int)chunks.size() - 1;
+    P.hcolptr = std::move(hcolptr);
+    P.fastplans.resize(ncol);
     if (int rc = upload(C, P.chunkptr, chunks.data(), chunks.size() * 4)) return rc;
     EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
     C->patterns.push_back(std::move(Pp));

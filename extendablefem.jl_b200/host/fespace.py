@@ -63,6 +63,12 @@ class FESpace:
             scalar = g.cellnodes.astype(np.int64)
             nscalar = nn
             bscalar = g.bfacenodes.astype(np.int64)
+        elif g.dim == 1:
+            # 1D: the "edge" dof of P2 is the cell midpoint
+            mid = nn + np.arange(1, g.ncells + 1, dtype=np.int64)
+            scalar = np.concatenate([g.cellnodes.astype(np.int64), mid[:, None]], axis=1)
+            nscalar = nn + g.ncells
+            bscalar = g.bfacenodes.astype(np.int64)
         else:
             edgenodes, celledges = g.edges()
             scalar = np.concatenate([g.cellnodes.astype(np.int64), celledges.astype(np.int64) + nn], axis=1)
@@ -98,6 +104,9 @@ class FESpace:
         g = self.xgrid
         if self.fetype.order == 1:
             return g.coords
+        if g.dim == 1:
+            cn = g.cellnodes.astype(np.int64)
+            return np.concatenate([g.coords, 0.5 * (g.coords[cn[:, 0] - 1] + g.coords[cn[:, 1] - 1])])
         en = g.edges()[0].astype(np.int64)
         return np.concatenate([g.coords, 0.5 * (g.coords[en[:, 0] - 1] + g.coords[en[:, 1] - 1])])
 

@@ -17,8 +17,8 @@ MAXARGS = 4
 OP_ID, OP_GRAD, OP_DIV, OP_SYMGRAD_VOIGT = 0, 1, 2, 3
 
 EXPORTS = [
-    "extfem_ctx_create", "extfem_ctx_destroy", "extfem_last_error", "extfem_kernel_id", "extfem_synchronize",
-    "extfem_launch_count", "extfem_last_timings", "extfem_mesh_set", "extfem_mesh_update_coords",
+    "extfem_ctx_create", "extfem_ctx_destroy", "extfem_last_error", "extfem_kernel_id", "extfem_synchronize", "extfem_set_option",
+    "extfem_launch_count", "extfem_last_timings", "extfem_event_record", "extfem_event_elapsed_ms", "extfem_mesh_set", "extfem_mesh_update_coords",
     "extfem_space_set", "extfem_space_set_tables", "extfem_pattern_build", "extfem_pattern_dims",
     "extfem_pattern_get", "extfem_assemble_bilinear", "extfem_assemble_linear", "extfem_assemble_nonlinear",
     "extfem_quadrature_points", "extfem_values_get", "extfem_values_set", "extfem_device_ptrs",
@@ -256,6 +256,17 @@ class Engine:
         it, rr = C.c_int(), C.c_double()
         self._check(self.lib.extfem_cg(self.ctx, pattern, _p(bb), _p(x), C.c_double(rtol), int(maxit), C.byref(it), C.byref(rr)))
         return x, it.value, rr.value
+
+    def event_record(self, slot: int):
+        self._check(self.lib.extfem_event_record(self.ctx, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double()
+        self._check(self.lib.extfem_event_elapsed_ms(self.ctx, a, b, C.byref(ms)))
+        return ms.value
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.extfem_set_option(self.ctx, key.encode(), int(value)))
 
     def synchronize(self):
         self._check(self.lib.extfem_synchronize(self.ctx))

@@ -119,11 +119,18 @@ int extfem_ctx_destroy(extfem_ctx *ctx);
 const char *extfem_last_error(extfem_ctx *ctx);      /* ctx may be NULL: last global error    */
 int extfem_kernel_id(const char *name);              /* <0: EXTFEM_ERR_UNREGISTERED_KERNEL     */
 int extfem_synchronize(extfem_ctx *ctx);
+/* engine options: "fastpath" (default 1): 0 forces the generic two-phase path for every operator */
+int extfem_set_option(extfem_ctx *ctx, const char *key, int value);
 /* number of kernel launches issued by this context since creation (bench "gpu_launches") */
 int64_t extfem_launch_count(extfem_ctx *ctx);
 /* device time in ms of the phases of the last assemble call (CUDA events):
  * [0] local (cell) kernel, [1] gather kernel(s), [2] total incl. copies.  */
 int extfem_last_timings(extfem_ctx *ctx, double *ms3);
+
+/* user-level device timers (the reference wraps assemble! in TimerOutputs sections,
+ * src/solvers.jl:140): record event `slot` (0..15) on the context's stream / elapsed ms. */
+int extfem_event_record(extfem_ctx *ctx, int slot);
+int extfem_event_elapsed_ms(extfem_ctx *ctx, int slot_start, int slot_stop, double *ms);
 
 /* ---- grid:  xgrid[Coordinates], xgrid[CellNodes], xgrid[CellRegions], xgrid[CellVolumes]
  *      (bilinear_operator.jl:693-695) ------------------------------------------------------- */
