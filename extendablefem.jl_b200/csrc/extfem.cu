@@ -40,9 +40,11 @@ struct Space {
 };
 
 struct FastPlan {
-    bool ready = false;
+    bool ready = false, usable = false;
     int nchunks = 0;
-    DevBuf chunkptr, slotcol, warpniter, warpoff, rec;
+    int cls_start[FP_NCLASS + 1] = {};  // chunks are ordered by shared-memory size class
+    std::vector<int> cls_maxtot = std::vector<int>(FP_NCLASS, 0);
+    DevBuf chunklist, slotcol, slotoff, chunktot, warpniter, warpoff, rec;
 };
 
 struct Pattern {
@@ -89,7 +91,8 @@ struct Ctx {
     std::map<std::pair<int, int>, std::unique_ptr<DevQuad>> quads; // (dim, order)
     DevBuf custom_qw, custom_qx;
     DevBuf loc, bloc, sol, params_scratch, tab, geo, visit;
-    bool fast_enabled = true;
+    bool fast_enabled = true;   // option "fastpath"
+    bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator
     long long launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t uev[16] = {};
@@ -503,87 +506,194 @@ static int finish_timing(Ctx *ctx)
 }
 
 // ---- fast path (fastpath.cuh) --------------------------------------------------------------------
+// Plan of one diagonal block: columns sorted by adjacency signature inside windows, cut into chunks of FP_T
+// slots, chunks ordered by shared-memory class; lane-contiguous records per warp round.
 static int build_fast_plan(Ctx *ctx, Pattern &P, int b, int ns)
 {
     if (!P.fastplans[b]) P.fastplans[b] = std::make_unique<FastPlan>();
     FastPlan &F = *P.fastplans[b];
     if (F.ready) return 0;
+    F.ready = true;
     Space &S = *ctx->spaces[P.colspaces[b]];
     Mesh &M = *ctx->meshes[S.mesh];
-    const long long c0 = P.coloff[b], c1 = P.coloff[b + 1];
-    // chunks in block-local column indices
-    std::vector<int> chunks;
-    chunks.push_back(0);
-    long long k = c0;
-    while (k < c1) {
-        long long k2 = k, base = P.hcolptr[k];
-        while (k2 < c1 && k2 - k < FP_THREADS && P.hcolptr[k2 + 1] - base <= FP_MAXNNZ) ++k2;
-        if (k2 == k) return fail(ctx, EXTFEM_ERR_CAPACITY, "matrix column too long for the fast gather kernel");
-        chunks.push_back((int)(k2 - c0));
-        k = k2;
+    if (M.ncells >= (1ll << FP_CELLBITS) || ns > (1 << FP_KLBITS)) return 0; // record word 0 cannot hold cell | kl
+    const long long ncols = S.ndofs;
+    const long long *colptr = P.colptr.as<long long>() + P.coloff[b];
+    F.nchunks = (int)((ncols + FP_T - 1) / FP_T);
+    const long long nslots = (long long)F.nchunks * FP_T;
+    {
+        DevBuf key, key2, col, order, tmp;
+        if (int rc = ensure(ctx, key, ncols * 8)) return rc;
+        if (int rc = ensure(ctx, key2, ncols * 8)) return rc;
+        if (int rc = ensure(ctx, col, ncols * 4)) return rc;
+        if (int rc = ensure(ctx, order, ncols * 4)) return rc;
+        fp_key_kernel<<<nblocks(ncols, 256), 256, 0, ctx->stream>>>(ncols, S.adjptr.as<long long>(), S.adjloc.as<unsigned char>(),
+                                                                   key.as<unsigned long long>(), col.as<int>());
+        LAUNCHED(ctx);
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, key.as<unsigned long long>(), key2.as<unsigned long long>(), col.as<int>(),
+                                        order.as<int>(), ncols, 0, 64, ctx->stream);
+        if (int rc = ensure(ctx, tmp, tb)) return rc;
+        EXTFEM_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.as<unsigned long long>(), key2.as<unsigned long long>(),
+                                                               col.as<int>(), order.as<int>(), ncols, 0, 64, ctx->stream));
+        LAUNCHED(ctx);
+        if (int rc = ensure(ctx, F.slotcol, (size_t)nslots * 4)) return rc;
+        if (int rc = ensure(ctx, F.slotoff, (size_t)nslots * 4)) return rc;
+        if (int rc = ensure(ctx, F.chunktot, (size_t)F.nchunks * 4)) return rc;
+        if (int rc = ensure(ctx, F.warpniter, (size_t)F.nchunks * FP_W * 4)) return rc;
+        fp_chunk_kernel<<<F.nchunks, FP_T, 0, ctx->stream>>>(ncols, order.as<int>(), colptr, S.adjptr.as<long long>(), F.slotcol.as<int>(),
+                                                            F.slotoff.as<int>(), F.chunktot.as<int>(), F.warpniter.as<int>());
+        LAUNCHED(ctx);
+        EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    F.nchunks = (int)chunks.size() - 1;
-    if (int rc = upload(ctx, F.chunkptr, chunks.data(), chunks.size() * 4)) return rc;
-    DevBuf sig;
-    if (int rc = ensure(ctx, sig, (size_t)S.ndofs * 8)) return rc;
-    fp_signature_kernel<<<nblocks(S.ndofs, 256), 256, 0, ctx->stream>>>(S.ndofs, S.adjptr.as<long long>(), S.adjloc.as<unsigned char>(),
-                                                                       sig.as<unsigned long long>());
-    LAUNCHED(ctx);
-    if (int rc = ensure(ctx, F.slotcol, (size_t)F.nchunks * FP_THREADS * 4)) return rc;
-    if (int rc = ensure(ctx, F.warpniter, (size_t)F.nchunks * FP_WARPS * 4)) return rc;
-    fp_sort_kernel<<<F.nchunks, 512, 0, ctx->stream>>>(F.chunkptr.as<int>(), sig.as<unsigned long long>(), S.adjptr.as<long long>(),
-                                                      F.slotcol.as<int>(), F.warpniter.as<int>());
-    LAUNCHED(ctx);
-    EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
-    std::vector<int> hn((size_t)F.nchunks * FP_WARPS);
+    std::vector<int> hn((size_t)F.nchunks * FP_W), htot((size_t)F.nchunks);
     EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(hn.data(), F.warpniter.p, hn.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(htot.data(), F.chunktot.p, htot.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int> lists[FP_NCLASS];
+    for (int c = 0; c < F.nchunks; ++c) {
+        if (htot[c] > fp_cap(FP_NCLASS - 1)) return 0; // chunk exceeds the largest shared-memory class: generic path
+        int cls = 0;
+        while (htot[c] > fp_cap(cls)) ++cls;
+        lists[cls].push_back(c);
+        F.cls_maxtot[cls] = std::max(F.cls_maxtot[cls], htot[c]);
+    }
+    std::vector<int> all;
+    for (int c = 0; c < FP_NCLASS; ++c) {
+        F.cls_start[c] = (int)all.size();
+        all.insert(all.end(), lists[c].begin(), lists[c].end());
+    }
+    F.cls_start[FP_NCLASS] = (int)all.size();
+    if (int rc = upload(ctx, F.chunklist, all.data(), all.size() * 4)) return rc;
     const int rw = fp_rw(ns);
     std::vector<long long> hoff(hn.size());
     long long tot = 0;
     for (size_t i = 0; i < hn.size(); ++i) { hoff[i] = tot; tot += (long long)hn[i] * rw * 32; }
     if (int rc = upload(ctx, F.warpoff, hoff.data(), hoff.size() * 8)) return rc;
-    if (int rc = ensure(ctx, F.rec, (size_t)tot * 4)) return rc;
-    long long nslots = (long long)F.nchunks * FP_THREADS;
+    if (int rc = ensure(ctx, F.rec, (size_t)tot * 4 + 16)) return rc;
     fp_fill_kernel<unsigned char><<<nblocks(nslots, 256), 256, 0, ctx->stream>>>(
         nslots, ns, rw, P.NRpat, F.slotcol.as<int>(), F.warpniter.as<int>(), F.warpoff.as<long long>(), S.adjptr.as<long long>(),
         S.adjcell.as<int>(), S.adjloc.as<unsigned char>(), P.posmap[b]->as<unsigned char>() + P.rowlocoff[b], F.rec.as<unsigned>());
     LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
     EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    (void)M;
-    F.ready = true;
+    F.usable = true;
     return 0;
 }
 
-template <int DIM, int NS, int FORM>
-static int launch_fast(Ctx *ctx, Pattern &P, FastPlan &F, int b, const Prepared &R, const extfem_opdesc *d, int accumulate)
+template <int DIM, int GEO, class EV>
+static int launch_fast(Ctx *ctx, Pattern &P, FastPlan &F, int b, const Prepared &R, const extfem_opdesc *d, double geoscale,
+                       int accumulate)
 {
-    constexpr int NG = fp_ng(DIM, FORM);
+    constexpr int NG = fp_ng(DIM, GEO);
+    static_assert(NG == EV::NG, "geometry record / evaluator mismatch");
     Mesh &M = *R.mesh;
     if (int rc = ensure(ctx, ctx->geo, (size_t)M.ncells * NG * 8)) return rc;
     if (d->nregions > 0) if (int rc = upload(ctx, ctx->visit, d->regions, (size_t)d->nregions * 4)) return rc;
-    fp_geo_kernel<DIM, FORM><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(
-        M.ncells, M.coords.as<double>(), M.cellnodes.as<int>(), M.regions.as<int>(), M.vol.as<double>(), d->factor, d->nregions,
-        ctx->visit.as<int>(), ctx->geo.as<double>());
+    fp_geo_kernel<DIM, GEO><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(
+        M.ncells, M.coords.as<double>(), M.cellnodes.as<int>(), M.regions.as<int>(), M.vol.as<double>(), d->factor * geoscale,
+        d->nregions, ctx->visit.as<int>(), ctx->geo.as<double>());
     LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     FastArgs A;
-    A.plan.nchunks = F.nchunks; A.plan.chunkptr = F.chunkptr.as<int>(); A.plan.slotcol = F.slotcol.as<int>();
+    A.plan.chunklist = F.chunklist.as<int>(); A.plan.slotcol = F.slotcol.as<int>(); A.plan.slotoff = F.slotoff.as<int>();
+    A.plan.chunktot = F.chunktot.as<int>();
     A.plan.warpniter = F.warpniter.as<int>(); A.plan.warpoff = F.warpoff.as<long long>(); A.plan.rec = F.rec.as<unsigned>();
     A.colptr = P.colptr.as<long long>() + P.coloff[b];
     A.nzval = P.nzval.as<double>(); A.geo = ctx->geo.as<double>(); A.overwrite = !accumulate;
+    // One launch per shared-memory class.  The small class runs one warp group per chunk; the larger classes are
+    // limited by shared memory, so their local rows are split over two warp groups (vertex rows | other rows) when
+    // the element has both (EV::NS > EV::NV).
+    constexpr int NGRP_BIG = EV::NS > EV::NV ? 2 : 1;
+    auto k0 = fp_gather_kernel<EV, 1, 6>;
+    auto k1 = fp_gather_kernel<EV, NGRP_BIG, (NGRP_BIG == 2 ? 3 : 4)>;
+    auto k2 = fp_gather_kernel<EV, NGRP_BIG, (NGRP_BIG == 2 ? 3 : 3)>;
     static bool attr_set = false;
-    auto kern = fp_gather_kernel<NS, NG>;
     if (!attr_set) {
-        EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_DOUBLES * 8));
+        EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
+        EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
+        EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
         attr_set = true;
     }
-    kern<<<F.nchunks, FP_THREADS, FP_SMEM_DOUBLES * 8, ctx->stream>>>(A);
-    LAUNCHED(ctx);
+    for (int c = FP_NCLASS - 1; c >= 0; --c) { // longest-running class first
+        int n = F.cls_start[c + 1] - F.cls_start[c];
+        if (n == 0) continue;
+        A.chunk0 = F.cls_start[c];
+        const size_t smem = (size_t)F.cls_maxtot[c] * 8; // what the class actually needs
+        if (c == 0) k0<<<n, FP_T, smem, ctx->stream>>>(A);
+        else if (c == 1) k1<<<n, FP_T * NGRP_BIG, smem, ctx->stream>>>(A);
+        else k2<<<n, FP_T * NGRP_BIG, smem, ctx->stream>>>(A);
+        LAUNCHED(ctx);
+    }
     EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     return 0;
+}
+
+// reference tables S[kl][t][g] of the table evaluator, from the SAME quadrature rule / basis as the generic path
+static std::vector<double> fast_tables(const QuadRule &Q, int order, int dim, int form)
+{
+    std::vector<double> v, g;
+    ref_basis(order, dim, Q, v, g);
+    const int ns = nscalar_of(order, dim), ng = fp_ng(dim, form == FP_FORM_MASS ? FP_GEO_VOLUME : FP_GEO_METRIC);
+    std::vector<double> T((size_t)ng * ns * ns, 0.0);
+    for (int q = 0; q < Q.nq; ++q)
+        for (int t = 0; t < ns; ++t)
+            for (int kl = 0; kl < ns; ++kl) {
+                double *out = &T[((size_t)kl * ns + t) * ng];
+                if (form == FP_FORM_MASS) { out[0] += Q.w[q] * v[(size_t)q * ns + t] * v[(size_t)q * ns + kl]; continue; }
+                int gi = 0;
+                for (int dd = 0; dd < dim; ++dd)
+                    for (int ee = dd; ee < dim; ++ee, ++gi) {
+                        double a = g[((size_t)q * ns + t) * dim + dd] * g[((size_t)q * ns + kl) * dim + ee];
+                        if (ee != dd) a += g[((size_t)q * ns + t) * dim + ee] * g[((size_t)q * ns + kl) * dim + dd];
+                        out[gi] += Q.w[q] * a;
+                    }
+            }
+    return T;
+}
+
+// The closed-form evaluator hard-codes the P1/P2 basis and exact integration.  Before it is used, check it on the
+// host against the tables of the operator's actual quadrature rule / basis on a generic (non-degenerate) simplex;
+// any mismatch (different basis convention, inexact rule) keeps the table evaluator.
+template <int DIM, int ORDER>
+static bool verify_bary_against_tables(const std::vector<double> &T)
+{
+    constexpr int NV = DIM + 1, NS = ORDER == 1 ? NV : NV * (NV + 1) / 2, NG = DIM * (DIM + 1) / 2;
+    // gradients of barycentric coordinates for J^-1 = B (rows), a fixed generic matrix
+    double B[3][3] = {{1.3, -0.2, 0.1}, {0.4, 0.9, -0.3}, {-0.5, 0.25, 1.1}};
+    double L[NV][DIM];
+    for (int x = 0; x < DIM; ++x) {
+        double s = 0;
+        for (int r = 0; r < DIM; ++r) { L[r + 1][x] = B[r][x]; s -= B[r][x]; }
+        L[0][x] = s;
+    }
+    double G[NG], Dg[NG], Mfull[NV][NV];
+    int o = 0;
+    for (int dd = 0; dd < DIM; ++dd)
+        for (int ee = dd; ee < DIM; ++ee) {
+            double s = 0;
+            for (int x = 0; x < DIM; ++x) s += B[dd][x] * B[ee][x];
+            G[o++] = s;
+        }
+    for (int a = 0; a < NV; ++a)
+        for (int c = a + 1; c < NV; ++c) {
+            double s = 0;
+            for (int x = 0; x < DIM; ++x) s += L[a][x] * L[c][x];
+            Dg[fp_pair_index<DIM>(a, c)] = s * fp_bary_scale(DIM, ORDER);
+        }
+    fp_bary_expand<DIM>(Dg, Mfull);
+    double scale = 0, err = 0;
+    for (int kl = 0; kl < NS; ++kl)
+        for (int t = 0; t < NS; ++t) {
+            double ref = 0;
+            for (int g = 0; g < NG; ++g) ref += G[g] * T[((size_t)kl * NS + t) * NG + g];
+            double got = fp_bary_acc<DIM, ORDER>(t, kl, Mfull, 0.0);
+            scale = std::max(scale, std::fabs(ref));
+            err = std::max(err, std::fabs(ref - got));
+        }
+    return err <= 1e-13 * scale;
 }
 
 // fast paths for the headline configurations; *fast == false -> generic path
@@ -604,6 +714,10 @@ static int try_fast_bilinear(Ctx *ctx, Pattern &P, const Prepared &R, const extf
     if (d->test_op[0] == EXTFEM_OP_GRAD && d->ansatz_op[0] == EXTFEM_OP_GRAD) form = FP_FORM_LAPLACE;
     else if (d->test_op[0] == EXTFEM_OP_ID && d->ansatz_op[0] == EXTFEM_OP_ID) form = FP_FORM_MASS;
     else return 0;
+    const int dim = op.dim, ns = S.nscalar;
+    if (int rc = build_fast_plan(ctx, P, b, ns)) return rc;
+    FastPlan &F = *P.fastplans[b];
+    if (!F.usable) return 0;
     // other column blocks of the pattern are not touched by this operator: zero them when overwriting
     if (!accumulate && P.colspaces.size() > 1) {
         for (size_t c = 0; c < P.colspaces.size(); ++c) {
@@ -612,43 +726,35 @@ static int try_fast_bilinear(Ctx *ctx, Pattern &P, const Prepared &R, const extf
             EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(P.nzval.as<double>() + n0, 0, (size_t)(n1 - n0) * 8, ctx->stream));
         }
     }
-    const int dim = op.dim, ns = S.nscalar;
-    if (int rc = build_fast_plan(ctx, P, b, ns)) return rc;
-    // reference tables S[g][t][kl] from the SAME quadrature rule / basis as the generic path
-    {
-        QuadRule Q;
-        Q.dim = dim; Q.nq = op.nq;
-        Q.w.resize(op.nq); Q.x.resize((size_t)op.nq * dim);
-        EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.w.data(), op.qw, op.nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.x.data(), op.qx, (size_t)op.nq * dim * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-        std::vector<double> v, g;
-        ref_basis(S.order, dim, Q, v, g);
-        const int ng = fp_ng(dim, form);
-        std::vector<double> T((size_t)ng * ns * ns, 0.0);
-        for (int q = 0; q < Q.nq; ++q)
-            for (int t = 0; t < ns; ++t)
-                for (int kl = 0; kl < ns; ++kl) {
-                    if (form == FP_FORM_MASS) { T[(size_t)t * ns + kl] += Q.w[q] * v[(size_t)q * ns + t] * v[(size_t)q * ns + kl]; continue; }
-                    int gi = 0;
-                    for (int dd = 0; dd < dim; ++dd)
-                        for (int ee = dd; ee < dim; ++ee, ++gi) {
-                            double a = g[((size_t)q * ns + t) * dim + dd] * g[((size_t)q * ns + kl) * dim + ee];
-                            if (ee != dd) a += g[((size_t)q * ns + t) * dim + ee] * g[((size_t)q * ns + kl) * dim + dd];
-                            T[((size_t)gi * ns + t) * ns + kl] += Q.w[q] * a;
-                        }
-                }
-        EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_fp_S, T.data(), T.size() * 8, 0, cudaMemcpyHostToDevice, ctx->stream));
-        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    FastPlan &F = *P.fastplans[b];
+    QuadRule Q;
+    Q.dim = dim; Q.nq = op.nq;
+    Q.w.resize(op.nq); Q.x.resize((size_t)op.nq * dim);
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.w.data(), op.qw, op.nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.x.data(), op.qx, (size_t)op.nq * dim * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<double> T = fast_tables(Q, S.order, dim, form);
     int rc = -1;
-#define FP_CASE(D, N, FRM) if (dim == D && ns == N && form == FRM) rc = launch_fast<D, N, FRM>(ctx, P, F, b, R, d, accumulate);
-    FP_CASE(1, 2, FP_FORM_LAPLACE) FP_CASE(1, 3, FP_FORM_LAPLACE) FP_CASE(2, 3, FP_FORM_LAPLACE) FP_CASE(2, 6, FP_FORM_LAPLACE)
-    FP_CASE(3, 4, FP_FORM_LAPLACE) FP_CASE(3, 10, FP_FORM_LAPLACE)
-    FP_CASE(1, 2, FP_FORM_MASS) FP_CASE(1, 3, FP_FORM_MASS) FP_CASE(2, 3, FP_FORM_MASS) FP_CASE(2, 6, FP_FORM_MASS)
-    FP_CASE(3, 4, FP_FORM_MASS) FP_CASE(3, 10, FP_FORM_MASS)
-#undef FP_CASE
+    // closed-form barycentric evaluators (Laplace, P1/P2, 2D/3D), verified against the tables
+    if (form == FP_FORM_LAPLACE && ctx->bary_enabled) {
+#define FP_BARY(D, O) \
+        if (rc == -1 && dim == D && S.order == O && verify_bary_against_tables<D, O>(T)) \
+            rc = launch_fast<D, FP_GEO_BARY, EvalBary<D, O>>(ctx, P, F, b, R, d, fp_bary_scale(D, O), accumulate);
+        FP_BARY(3, 2) FP_BARY(3, 1) FP_BARY(2, 2) FP_BARY(2, 1)
+#undef FP_BARY
+    }
+    if (rc == -1) {
+        EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_fp_S, T.data(), T.size() * 8, 0, cudaMemcpyHostToDevice, ctx->stream));
+#define FP_TAB(D, N, FRM, GEO) \
+        if (rc == -1 && dim == D && ns == N && form == FRM) \
+            rc = launch_fast<D, GEO, EvalTable<N, fp_ng(D, GEO), D + 1>>(ctx, P, F, b, R, d, 1.0, accumulate);
+        FP_TAB(1, 2, FP_FORM_LAPLACE, FP_GEO_METRIC) FP_TAB(1, 3, FP_FORM_LAPLACE, FP_GEO_METRIC)
+        FP_TAB(2, 3, FP_FORM_LAPLACE, FP_GEO_METRIC) FP_TAB(2, 6, FP_FORM_LAPLACE, FP_GEO_METRIC)
+        FP_TAB(3, 4, FP_FORM_LAPLACE, FP_GEO_METRIC) FP_TAB(3, 10, FP_FORM_LAPLACE, FP_GEO_METRIC)
+        FP_TAB(1, 2, FP_FORM_MASS, FP_GEO_VOLUME) FP_TAB(1, 3, FP_FORM_MASS, FP_GEO_VOLUME)
+        FP_TAB(2, 3, FP_FORM_MASS, FP_GEO_VOLUME) FP_TAB(2, 6, FP_FORM_MASS, FP_GEO_VOLUME)
+        FP_TAB(3, 4, FP_FORM_MASS, FP_GEO_VOLUME) FP_TAB(3, 10, FP_FORM_MASS, FP_GEO_VOLUME)
+#undef FP_TAB
+    }
     if (rc == -1) return 0; // no instantiation: generic path
     if (rc) return rc;
     *fast = true;
@@ -740,6 +846,7 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
 {
     CTX_GUARD(ctx);
     if (key && !strcmp(key, "fastpath")) { C->fast_enabled = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "fastpath_closed_form")) { C->bary_enabled = value != 0; return EXTFEM_OK; }
     return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("unknown option ") + (key ? key : "(null)"));
 }
 

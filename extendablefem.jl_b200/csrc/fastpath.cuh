@@ -1,21 +1,32 @@
-// fastpath.cuh -- fused assembly kernels for the headline configurations.
+// fastpath.cuh -- fused owner-computes assembly kernels for the headline configurations
+// (DESIGN.md section 4).
 //
 // Scalar H1 Lagrange spaces on affine simplices with the standard kernel:
-//     Laplace  BilinearOperator([grad(u)])   A_loc[i,j] = sum_{d<=e} G_de * S^{de}[i][j]
-//     mass     BilinearOperator([id(u)])     A_loc[i,j] = |T| f  * S^{0}[i][j]
-// where G = factor |T| J^-1 J^-T is the per-cell geometry factor (phase 0, coalesced) and
-// S^{de}[i][j] = sum_q w_q d_d phi_i(q) d_e phi_j(q) (+ transposed term) are reference tables
-// computed on the host WITH THE SAME quadrature rule and reference basis as the generic path,
-// i.e. the reference's sum over quadrature points (bilinear_operator.jl:876-916) reassociated.
+//     Laplace  BilinearOperator([grad(u)])   A_loc = factor |T| sum_q w_q grad phi_i . grad phi_j
+//     mass     BilinearOperator([id(u)])     A_loc = factor |T| sum_q w_q phi_i phi_j
+// i.e. the reference's sum over quadrature points (bilinear_operator.jl:876-916) reassociated into
+// (per-cell geometry factor) x (reference-element table).
 //
-// The matrix is produced by an OWNER-COMPUTES gather without atomics and without an
-// intermediate cell-local buffer: one thread owns one CSC column, computes the local column of
-// every adjacent cell on the fly and accumulates it into shared memory laid out as the CSC
-// segment of its CTA's contiguous column chunk, which is then written with unit-stride stores
-// (each nzval byte is written exactly once).  Inside a chunk, columns are assigned to lanes
-// sorted by a signature of their adjacency so that warps are (nearly) divergence-free, and the
-// per-(column, cell) records are stored warp-transposed (ELL per warp) so every record load is a
-// fully coalesced 128-byte access per word.
+// The matrix is produced by an OWNER-COMPUTES gather without atomics and without a cell-local
+// buffer: one thread owns one CSC column, computes the local column of every adjacent cell on the
+// fly and accumulates it into shared memory laid out as the CSC segment of its CTA's contiguous
+// column chunk, which is then written with unit-stride stores (every nzval byte is written exactly
+// once).  Columns are sorted by a signature of their adjacency (number of cells + local indices) inside
+// windows of FP_WINDOW consecutive columns and cut into chunks of FP_T columns, so that the lanes of a
+// warp own structurally identical columns and run (nearly) divergence-free; chunks are grouped into
+// shared-memory size classes so that short (edge-dof) and long (vertex-dof) columns both reach high
+// occupancy, and where shared memory limits occupancy the local rows are split by entity class
+// (vertex rows | edge rows: disjoint global rows) over two warp groups that share the accumulators.
+// The per-(column, cell) records are stored lane-contiguous per warp round so that one vector load per
+// lane fetches a record and a warp reads one contiguous block.
+//
+// Two evaluators produce the local column:
+//   EvalTable<NS,NG>   v[t] = sum_g G[g] S[kl][t][g], reference tables S computed on the host WITH THE
+//                      SAME quadrature rule and basis as the generic path (any form / dimension);
+//   EvalBary<DIM,ORD>  closed form for the Laplace form of P1/P2 in terms of the barycentric Gram
+//                      matrix D_ab = factor |T| grad(lambda_a).grad(lambda_b): every P2 entry is a
+//                      combination of <= 4 D-values with small integer coefficients.  The host checks
+//                      it against the tables before it is used (extfem.cu: verify_bary_against_tables).
 #pragma once
 #include "common.cuh"
 
@@ -56,21 +67,103 @@ static inline int launch_cell_volumes(cudaStream_t st, int dim, long long ncells
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int FP_THREADS = 448;         // columns (threads) per chunk: 14 warps
-constexpr int FP_WARPS = FP_THREADS / 32;
-constexpr int FP_MAXNNZ = 11008;        // CSC entries per chunk held in shared memory
-constexpr int FP_SMEM_DOUBLES = FP_MAXNNZ + FP_MAXNNZ / 16 + 8;
+constexpr int FP_T = 128;               // columns per chunk (threads per warp group)
+constexpr int FP_W = FP_T / 32;
+constexpr int FP_WINDOW = 2048;         // columns per sorting window (multiple of FP_T)
+constexpr int FP_NCLASS = 3;            // shared-memory size classes of chunks (doubles per chunk)
+constexpr int FP_CAP0 = 3584, FP_CAP1 = 5632, FP_CAP2 = 8448;
+__host__ __device__ constexpr int fp_cap(int cls) { return cls == 0 ? FP_CAP0 : (cls == 1 ? FP_CAP1 : FP_CAP2); }
+constexpr int FP_KLBITS = 4, FP_CELLBITS = 32 - FP_KLBITS; // record word 0 = cell | kl << 28
 enum { FP_FORM_LAPLACE = 0, FP_FORM_MASS = 1 };
+enum { FP_GEO_METRIC = 0, FP_GEO_VOLUME = 1, FP_GEO_BARY = 2 };
 
-__host__ __device__ constexpr int fp_ng(int dim, int form) { return form == FP_FORM_MASS ? 1 : dim * (dim + 1) / 2; }
-// number of 32-bit words of one (column, cell) record: cell id, then 1 + NS bytes (kl, pos[NS])
-__host__ __device__ constexpr int fp_rw(int ns) { return 1 + (1 + ns + 3) / 4; }
+__host__ __device__ constexpr int fp_ng(int dim, int geo) { return geo == FP_GEO_VOLUME ? 1 : dim * (dim + 1) / 2; }
+// 32-bit words of one (column, cell) record: word 0 = cell | kl << 28, then NS position bytes
+__host__ __device__ constexpr int fp_rw(int ns) { return 1 + (ns + 3) / 4; }
 
-// reference tables S[g][t][kl] of the current launch (uploaded per operator)
+// reference tables S[kl][t][g] of the current launch (uploaded per operator)
 __constant__ double c_fp_S[6 * 10 * 10];
 
-// phase 0: per-cell geometry factor  G = factor * |T| * J^-1 J^-T  (upper triangle) or factor*|T|
-template <int DIM, int FORM>
+// ---- local edge tables (ExtendableGrids local_celledgenodes order; grids.py TRI_EDGES / TET_EDGES) ------
+template <int DIM> __host__ __device__ constexpr int fp_edge_a(int e)
+{
+    if (DIM == 1) return 0;
+    if (DIM == 2) return e;                       // (0,1) (1,2) (2,0)
+    return e < 3 ? 0 : (e < 5 ? 1 : 2);           // (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+}
+template <int DIM> __host__ __device__ constexpr int fp_edge_b(int e)
+{
+    if (DIM == 1) return 1;
+    if (DIM == 2) return (e + 1) % 3;
+    return e < 3 ? e + 1 : (e < 5 ? e - 1 : 3);
+}
+// index of the off-diagonal D_ab (a < b) in the per-cell geometry record: pairs in lexicographic order
+template <int DIM> __host__ __device__ constexpr int fp_pair_index(int a, int b)
+{
+    // lexicographic rank of (a,b), a<b, among pairs of {0..DIM}
+    return a * (2 * DIM + 1 - a) / 2 + (b - a - 1);
+}
+
+// Closed-form local Laplace entry (t, kl) from the full symmetric barycentric Gram matrix M (already scaled:
+// P1: M = D; P2: M = D/5 in 3D, D/3 in 2D -- see fp_bary_scale), valid for DIM = 2, 3.
+//   P1:  A[t][kl] = D[t][kl]
+//   P2:  vertex-vertex  3 M_ii | -M_ij
+//        vertex i - edge (a,b)   c(i==a) M_ib + c(i==b) M_ia,  c = 3 | -1 (3D),  4 | 0 (2D)
+//        edge (a,b) - edge (c,d) w(a==c) M_bd + w(a==d) M_bc + w(b==c) M_ad + w(b==d) M_ac,  w = 8 | 4
+// (exact integrals of the barycentric polynomials: int l_i = 1/(d+1), int l_i l_j = (1+delta_ij)/((d+1)(d+2)))
+__host__ __device__ constexpr double fp_bary_scale(int dim, int order) { return order == 1 ? 1.0 : (dim == 3 ? 0.2 : 1.0 / 3.0); }
+
+template <int DIM, int ORDER>
+__host__ __device__ __forceinline__ double fp_bary_acc(int t, int kl, const double (&M)[DIM + 1][DIM + 1], double r)
+{
+    // returns r + A_loc[t][kl] as a chain of fused multiply-adds
+    constexpr int NV = DIM + 1;
+    if (ORDER == 1) return r + M[t][kl];
+    const bool tv = t < NV, kv = kl < NV;
+    if (tv && kv) return t == kl ? fma(3.0, M[t][t], r) : r - M[t][kl];
+    if (tv != kv) {
+        const int i = tv ? t : kl, e = (tv ? kl : t) - NV;
+        const int a = fp_edge_a<DIM>(e), b = fp_edge_b<DIM>(e);
+        if (DIM == 3) {
+            r = (i == a) ? fma(3.0, M[i][b], r) : r - M[i][b];
+            r = (i == b) ? fma(3.0, M[i][a], r) : r - M[i][a];
+        } else {
+            if (i == a) r = fma(4.0, M[i][b], r);
+            if (i == b) r = fma(4.0, M[i][a], r);
+        }
+        return r;
+    }
+    const int a = fp_edge_a<DIM>(t - NV), b = fp_edge_b<DIM>(t - NV), c = fp_edge_a<DIM>(kl - NV), d = fp_edge_b<DIM>(kl - NV);
+    r = fma(a == c ? 8.0 : 4.0, M[b][d], r);
+    r = fma(a == d ? 8.0 : 4.0, M[b][c], r);
+    r = fma(b == c ? 8.0 : 4.0, M[a][d], r);
+    r = fma(b == d ? 8.0 : 4.0, M[a][c], r);
+    return r;
+}
+
+// full symmetric M from the NG stored off-diagonals (rows of the Gram matrix of barycentric gradients sum to 0)
+template <int DIM>
+__host__ __device__ __forceinline__ void fp_bary_expand(const double (&G)[DIM * (DIM + 1) / 2], double (&M)[DIM + 1][DIM + 1])
+{
+#pragma unroll
+    for (int a = 0; a <= DIM; ++a)
+#pragma unroll
+        for (int b = a + 1; b <= DIM; ++b) M[a][b] = M[b][a] = G[fp_pair_index<DIM>(a, b)];
+#pragma unroll
+    for (int a = 0; a <= DIM; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b <= DIM; ++b)
+            if (b != a) s -= M[a][b];
+        M[a][a] = s;
+    }
+}
+
+// ---- phase 0: per-cell geometry record -------------------------------------------------------------
+//   FP_GEO_METRIC  f |T| J^-1 J^-T (upper triangle)      table Laplace
+//   FP_GEO_VOLUME  f |T|                                 mass
+//   FP_GEO_BARY    s f |T| grad(l_a).grad(l_b), a<b      closed-form Laplace (s = fp_bary_scale)
+template <int DIM, int GEO>
 __global__ void __launch_bounds__(256)
 fp_geo_kernel(long long ncells, const double *__restrict__ coords, const int *__restrict__ cellnodes,
               const int *__restrict__ regions, const double *__restrict__ vol, double factor, int nregions,
@@ -78,7 +171,7 @@ fp_geo_kernel(long long ncells, const double *__restrict__ coords, const int *__
 {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
-    constexpr int NG = fp_ng(DIM, FORM);
+    constexpr int NG = fp_ng(DIM, GEO);
     double f = factor * vol[c];
     if (nregions > 0) {
         int reg = regions[c], vis = 0;
@@ -86,8 +179,15 @@ fp_geo_kernel(long long ncells, const double *__restrict__ coords, const int *__
         if (!vis) f = 0.0;
     }
     double *g = geo + c * NG;
-    if (FORM == FP_FORM_MASS) { g[0] = f; return; }
-    const int *cn = cellnodes + c * (DIM + 1);
+    if (GEO == FP_GEO_VOLUME) { g[0] = f; return; }
+    int cn[DIM + 1];
+    if (DIM == 3) {
+        int4 q = __ldg(reinterpret_cast<const int4 *>(cellnodes) + c);
+        cn[0] = q.x; cn[1 % (DIM + 1)] = q.y; cn[2 % (DIM + 1)] = q.z; cn[3 % (DIM + 1)] = q.w;
+    } else {
+#pragma unroll
+        for (int r = 0; r <= DIM; ++r) cn[r] = cellnodes[c * (DIM + 1) + r];
+    }
     double A[DIM][DIM], B[DIM][DIM]; // B = A^-1 (rows = gradients of lambda_1..DIM)
     const double *p0 = coords + (size_t)cn[0] * DIM;
 #pragma unroll
@@ -116,165 +216,293 @@ fp_geo_kernel(long long ncells, const double *__restrict__ coords, const int *__
         B[I1][I2] = (A[0][I2] * A[I1][0] - A[0][0] * A[I1][I2]) * id;
         B[I2][I2] = (A[0][0] * A[I1][I1] - A[0][I1] * A[I1][0]) * id;
     }
-    int o = 0;
+    double out[NG];
+    if (GEO == FP_GEO_METRIC) {
+        int o = 0;
 #pragma unroll
-    for (int d = 0; d < DIM; ++d)
+        for (int d = 0; d < DIM; ++d)
 #pragma unroll
-        for (int e = d; e < DIM; ++e) {
+            for (int e = d; e < DIM; ++e) {
+                double s = 0.0;
+#pragma unroll
+                for (int x = 0; x < DIM; ++x) s += B[d][x] * B[e][x];
+                out[o++] = f * s;
+            }
+    } else {
+        // gradients of the barycentric coordinates: l_r = row r-1 of B (r >= 1), l_0 = -sum
+        double L[DIM + 1][DIM];
+#pragma unroll
+        for (int x = 0; x < DIM; ++x) {
             double s = 0.0;
 #pragma unroll
-            for (int x = 0; x < DIM; ++x) s += B[d][x] * B[e][x];
-            g[o++] = f * s;
+            for (int r = 0; r < DIM; ++r) { L[r + 1][x] = B[r][x]; s -= B[r][x]; }
+            L[0][x] = s;
         }
+#pragma unroll
+        for (int a = 0; a <= DIM; ++a)
+#pragma unroll
+            for (int b = a + 1; b <= DIM; ++b) {
+                double s = 0.0;
+#pragma unroll
+                for (int x = 0; x < DIM; ++x) s += L[a][x] * L[b][x];
+                out[fp_pair_index<DIM>(a, b)] = f * s;   // f already contains fp_bary_scale (host)
+            }
+    }
+    if (NG % 2 == 0) {
+#pragma unroll
+        for (int o = 0; o < NG; o += 2) reinterpret_cast<double2 *>(g)[o / 2] = make_double2(out[o], out[(o + 1) % NG]);
+    } else {
+#pragma unroll
+        for (int o = 0; o < NG; ++o) g[o] = out[o];
+    }
 }
 
+// ---- plan ------------------------------------------------------------------------------------------
 struct FastPlanDev {
-    int nchunks;
-    const int *chunkptr;          // [nchunks+1] column ranges
-    const int *slotcol;           // [nchunks*FP_THREADS] column of sorted slot (-1: idle)
-    const int *warpniter;         // [nchunks*FP_WARPS]
-    const long long *warpoff;     // [nchunks*FP_WARPS] offset (in u32 words) of the warp's record block
-    const unsigned *rec;          // warp-transposed records
+    const int *chunklist;         // [nchunks] chunk ids ordered by shared-memory class
+    const int *slotcol;           // [nchunks*FP_T] column (block-local) of the slot, sorted by signature; -1: idle
+    const int *slotoff;           // [nchunks*FP_T] offset of the slot's column segment in the chunk's accumulators
+    const int *chunktot;          // [nchunks] accumulator doubles of the chunk
+    const int *warpniter;         // [nchunks*FP_W]
+    const long long *warpoff;     // [nchunks*FP_W] offset (in u32 words) of the warp's record block
+    const unsigned *rec;          // records: [round][lane][RW] per warp
 };
 
 struct FastArgs {
     FastPlanDev plan;
-    const long long *colptr;
+    const long long *colptr;      // of the column block
     double *nzval;
     const double *geo;
     int overwrite;
+    int chunk0;                   // first entry of chunklist of this launch (class)
 };
 
-__device__ __forceinline__ int fp_pad(int i) { return i + (i >> 4); }
+// ---- evaluators: cur[t] += A_loc[t][KL] for local rows t in [T0, T1) ---------------------------------
+template <int NS_, int NG_, int NV_>
+struct EvalTable {
+    static constexpr int NS = NS_, NG = NG_, NV = NV_;
+    template <int KL, int T0, int T1>
+    __device__ __forceinline__ static void column(const double (&G)[NG], double (&cur)[NS])
+    {
+#pragma unroll
+        for (int t = T0; t < T1; ++t) {
+            double s = cur[t];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) s = fma(G[g], c_fp_S[(KL * NS + t) * NG + g], s);
+            cur[t] = s;
+        }
+    }
+};
 
-// local column KL of the cell matrix, accumulated at the byte positions of the record
-template <int NS, int NG, int KL>
-__device__ __forceinline__ void fp_accumulate(const double (&G)[NG], double *__restrict__ a, int aoff, const unsigned (&w)[fp_rw(NS)])
+template <int DIM, int ORDER>
+struct EvalBary {
+    static constexpr int NV = DIM + 1, NS = ORDER == 1 ? DIM + 1 : (DIM + 1) * (DIM + 2) / 2, NG = DIM * (DIM + 1) / 2;
+    template <int KL, int T0, int T1>
+    __device__ __forceinline__ static void column(const double (&G)[NG], double (&cur)[NS])
+    {
+        double M[DIM + 1][DIM + 1];
+        fp_bary_expand<DIM>(G, M);
+#pragma unroll
+        for (int t = T0; t < T1; ++t) cur[t] = fp_bary_acc<DIM, ORDER>(t, KL, M, cur[t]);
+    }
+};
+
+// Column KL of the local matrix, rows [T0, T1), accumulated at the byte positions of the record.  The positions
+// of one (column, cell) pair are distinct rows of the column, so all loads are issued before all stores: the
+// read-modify-write chains run concurrently instead of being serialised by possible aliasing.
+template <class EV, int KL, int T0, int T1>
+__device__ __forceinline__ void fp_column_rmw(const double (&G)[EV::NG], double *__restrict__ a, const unsigned (&w)[fp_rw(EV::NS)])
 {
+    if (KL < EV::NS) {
+        constexpr int K = KL < EV::NS ? KL : 0;
+        double cur[EV::NS];
+        int pos[EV::NS];
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
-        double v = 0.0;
+        for (int t = T0; t < T1; ++t) {
+            pos[t] = (w[1 + t / 4] >> (8 * (t % 4))) & 0xff;
+            cur[t] = a[pos[t]];
+        }
+        EV::template column<K, T0, T1>(G, cur);
 #pragma unroll
-        for (int g = 0; g < NG; ++g) v += G[g] * c_fp_S[(g * NS + t) * NS + KL];
-        const int byte = 1 + t;                                   // byte 0 of word 1 is kl
-        const int pos = (w[1 + byte / 4] >> (8 * (byte % 4))) & 0xff;
-        a[fp_pad(aoff + pos)] += v;
+        for (int t = T0; t < T1; ++t) a[pos[t]] = cur[t];
     }
 }
 
-template <int NS, int NG, int KL>
-struct FpSwitch {
-    __device__ __forceinline__ static void run(int kl, const double (&G)[NG], double *a, int aoff, const unsigned (&w)[fp_rw(NS)])
-    {
-        if (kl == KL) fp_accumulate<NS, NG, KL>(G, a, aoff, w);
-        else FpSwitch<NS, NG, KL + 1>::run(kl, G, a, aoff, w);
+template <class EV, int T0, int T1>
+__device__ __forceinline__ void fp_dispatch(int kl, const double (&G)[EV::NG], double *__restrict__ a, const unsigned (&w)[fp_rw(EV::NS)])
+{
+    static_assert(EV::NS <= 10, "fp_dispatch handles up to 10 local dofs");
+    switch (kl) {
+    case 0: fp_column_rmw<EV, 0, T0, T1>(G, a, w); break;
+    case 1: fp_column_rmw<EV, 1, T0, T1>(G, a, w); break;
+    case 2: fp_column_rmw<EV, 2, T0, T1>(G, a, w); break;
+    case 3: fp_column_rmw<EV, 3, T0, T1>(G, a, w); break;
+    case 4: fp_column_rmw<EV, 4, T0, T1>(G, a, w); break;
+    case 5: fp_column_rmw<EV, 5, T0, T1>(G, a, w); break;
+    case 6: fp_column_rmw<EV, 6, T0, T1>(G, a, w); break;
+    case 7: fp_column_rmw<EV, 7, T0, T1>(G, a, w); break;
+    case 8: fp_column_rmw<EV, 8, T0, T1>(G, a, w); break;
+    case 9: fp_column_rmw<EV, 9, T0, T1>(G, a, w); break;
     }
-};
-template <int NS, int NG>
-struct FpSwitch<NS, NG, NS> {
-    __device__ __forceinline__ static void run(int, const double (&)[NG], double *, int, const unsigned (&)[fp_rw(NS)]) {}
-};
+}
 
-template <int NS, int NG>
-__global__ void __launch_bounds__(FP_THREADS, 2)
+template <int RW>
+__device__ __forceinline__ void fp_load_rec(const unsigned *p, unsigned (&w)[RW])
+{
+    if (RW == 4) {
+        uint4 q = __ldcs(reinterpret_cast<const uint4 *>(p));
+        w[0] = q.x; w[1 % RW] = q.y; w[2 % RW] = q.z; w[3 % RW] = q.w;
+    } else if (RW == 2) {
+        uint2 q = __ldcs(reinterpret_cast<const uint2 *>(p));
+        w[0] = q.x; w[1 % RW] = q.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < RW; ++j) w[j] = __ldcs(p + j);
+    }
+}
+
+template <int NG>
+__device__ __forceinline__ void fp_load_geo(const double *__restrict__ geo, int cell, double (&G)[NG])
+{
+    const double *gp = geo + (size_t)cell * NG;
+    if (NG % 2 == 0) {
+#pragma unroll
+        for (int g = 0; g < NG; g += 2) {
+            double2 t2 = __ldg(reinterpret_cast<const double2 *>(gp + g));
+            G[g] = t2.x; G[(g + 1) % NG] = t2.y;
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) G[g] = __ldg(gp + g);
+    }
+}
+
+// rounds of one warp over local rows [T0, T1): software pipeline with word 0 (cell | kl) two rounds ahead -- which
+// also pulls the record's line into L1 --, full record and geometry one round ahead, double-buffered by parity
+template <class EV, int T0, int T1>
+__device__ __forceinline__ void fp_rounds(const unsigned *__restrict__ rec, int niter, const double *__restrict__ geo, double *__restrict__ a)
+{
+    constexpr int NG = EV::NG, RW = fp_rw(EV::NS);
+    constexpr unsigned CELLMASK = (1u << FP_CELLBITS) - 1u, NONE = 0xffffffffu;
+    unsigned w[2][RW];
+    double G[2][NG];
+    unsigned c1 = NONE; // word 0 of round r+1
+    if (niter > 0) {
+        fp_load_rec<RW>(rec, w[0]);
+        if (w[0][0] != NONE) fp_load_geo<NG>(geo, w[0][0] & CELLMASK, G[0]);
+    }
+    if (niter > 1) c1 = __ldcs(rec + (size_t)32 * RW);
+#define FP_ROUND(CUR, NXT)                                                                                  \
+    {                                                                                                       \
+        unsigned c2 = NONE;                                                                                 \
+        if (r + 1 < niter) {                                                                                \
+            if (c1 != NONE) fp_load_geo<NG>(geo, c1 & CELLMASK, G[NXT]);                                    \
+            fp_load_rec<RW>(rec + (size_t)(r + 1) * 32 * RW, w[NXT]);                                       \
+            if (r + 2 < niter) c2 = __ldcs(rec + (size_t)(r + 2) * 32 * RW);                                \
+        }                                                                                                   \
+        if (w[CUR][0] != NONE) fp_dispatch<EV, T0, T1>((int)(w[CUR][0] >> FP_CELLBITS), G[CUR], a, w[CUR]); \
+        c1 = c2;                                                                                            \
+    }
+    int r = 0;
+    for (; r + 1 < niter; r += 2) {
+        FP_ROUND(0, 1)
+        ++r;
+        FP_ROUND(1, 0)
+        --r;
+    }
+    if (r < niter) FP_ROUND(0, 1)
+#undef FP_ROUND
+}
+
+// NGRP == 2: warp group 0 accumulates the vertex rows [0, NV), group 1 the remaining rows [NV, NS) of the same
+// columns; the two groups touch disjoint global rows, hence disjoint accumulators, and need no synchronisation.
+template <class EV, int NGRP, int MINB>
+__global__ void __launch_bounds__(FP_T * NGRP, MINB)
 fp_gather_kernel(const __grid_constant__ FastArgs A)
 {
     extern __shared__ double acc[];
-    constexpr int RW = fp_rw(NS);
-    const int chunk = blockIdx.x;
-    const int k0 = A.plan.chunkptr[chunk], k1 = A.plan.chunkptr[chunk + 1];
-    const long long base = A.colptr[k0];
-    const int n = (int)(A.colptr[k1] - base);
-    if (A.overwrite)
-        for (int i = threadIdx.x; i < n; i += FP_THREADS) acc[fp_pad(i)] = 0.0;
-    else
-        for (int i = threadIdx.x; i < n; i += FP_THREADS) acc[fp_pad(i)] = A.nzval[base + i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k = A.plan.slotcol[(size_t)chunk * FP_THREADS + threadIdx.x];
-    const int niter = A.plan.warpniter[chunk * FP_WARPS + warp];
-    const unsigned *rec = A.plan.rec + A.plan.warpoff[chunk * FP_WARPS + warp] + lane;
-    const int aoff = k >= 0 ? (int)(A.colptr[k] - base) : 0;
-    unsigned w[RW], wn[RW];
-    if (niter > 0) {
-#pragma unroll
-        for (int j = 0; j < RW; ++j) wn[j] = __ldg(rec + j * 32);
+    __shared__ long long s_cp[FP_T];
+    __shared__ int s_len[FP_T], s_off[FP_T];
+    constexpr int NS = EV::NS, RW = fp_rw(NS), NT = FP_T * NGRP;
+    const int chunk = A.plan.chunklist[A.chunk0 + blockIdx.x];
+    const int n = A.plan.chunktot[chunk];
+    const int slot = threadIdx.x % FP_T, grp = threadIdx.x / FP_T;
+    const int lane = threadIdx.x & 31, warp = slot >> 5;
+    const int k = A.plan.slotcol[(size_t)chunk * FP_T + slot];
+    const int off = A.plan.slotoff[(size_t)chunk * FP_T + slot];
+    if (grp == 0) {
+        long long c0 = 0;
+        int len = 0;
+        if (k >= 0) { c0 = A.colptr[k]; len = (int)(A.colptr[k + 1] - c0); }
+        s_cp[slot] = c0; s_len[slot] = len; s_off[slot] = off;
     }
-    for (int r = 0; r < niter; ++r) {
-#pragma unroll
-        for (int j = 0; j < RW; ++j) w[j] = wn[j];
-        if (r + 1 < niter) {
-#pragma unroll
-            for (int j = 0; j < RW; ++j) wn[j] = __ldg(rec + ((size_t)(r + 1) * RW + j) * 32);
+    if (A.overwrite) {
+        for (int i = threadIdx.x; i < n; i += NT) acc[i] = 0.0;
+        __syncthreads();
+    } else {
+        __syncthreads();
+        for (int s = threadIdx.x >> 5; s < FP_T; s += NT / 32) {
+            const long long c0 = s_cp[s];
+            const int len = s_len[s], o = s_off[s];
+            for (int i = lane; i < len; i += 32) acc[o + i] = A.nzval[c0 + i];
         }
-        const int cell = (int)w[0];
-        if (cell < 0) continue;
-        double G[NG];
-        const double *gp = A.geo + (size_t)cell * NG;
-        if (NG % 2 == 0) {
-#pragma unroll
-            for (int g = 0; g < NG; g += 2) {
-                double2 t2 = __ldg(reinterpret_cast<const double2 *>(gp + g));
-                G[g] = t2.x; G[(g + 1) % NG] = t2.y;
-            }
-        } else {
-#pragma unroll
-            for (int g = 0; g < NG; ++g) G[g] = __ldg(gp + g);
-        }
-        const int kl = w[1] & 0xff;
-        FpSwitch<NS, NG, 0>::run(kl, G, acc, aoff, w);
+        __syncthreads();
     }
+    const int niter = A.plan.warpniter[chunk * FP_W + warp];
+    const unsigned *rec = A.plan.rec + A.plan.warpoff[chunk * FP_W + warp] + lane * RW;
+    double *a = acc + off;
+    if (NGRP == 1) fp_rounds<EV, 0, NS>(rec, niter, A.geo, a);
+    else if (grp == 0) fp_rounds<EV, 0, EV::NV>(rec, niter, A.geo, a);
+    else fp_rounds<EV, EV::NV, NS>(rec, niter, A.geo, a);
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += FP_THREADS) A.nzval[base + i] = acc[fp_pad(i)];
+    for (int s = threadIdx.x >> 5; s < FP_T; s += NT / 32) {
+        const long long c0 = s_cp[s];
+        const int len = s_len[s], o = s_off[s];
+        for (int i = lane; i < len; i += 32) __stcs(A.nzval + c0 + i, acc[o + i]);
+    }
 }
 
 // ---- plan construction (setup, once per pattern) -----------------------------------------------
-__global__ void fp_signature_kernel(long long ncols, const long long *__restrict__ adjptr, const unsigned char *__restrict__ adjloc,
-                                    unsigned long long *__restrict__ sig)
+// sort key: window | number of adjacent cells | hash of the local indices; the radix sort is stable, so equal
+// signatures stay in column order
+__global__ void fp_key_kernel(long long ncols, const long long *__restrict__ adjptr, const unsigned char *__restrict__ adjloc,
+                              unsigned long long *__restrict__ key, int *__restrict__ col)
 {
     long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= ncols) return;
     long long p0 = adjptr[k], p1 = adjptr[k + 1];
     unsigned long long h = 1469598103934665603ull;
     for (long long p = p0; p < p1; ++p) { h ^= adjloc[p]; h *= 1099511628211ull; }
-    sig[k] = ((unsigned long long)(p1 - p0) << 48) | (h & 0xffffffffffffull);
+    unsigned long long cnt = (unsigned long long)min((long long)255, p1 - p0);
+    key[k] = ((unsigned long long)(k / FP_WINDOW) << 42) | (cnt << 34) | ((h ^ (h >> 34)) & ((1ull << 34) - 1));
+    col[k] = (int)k;
 }
 
-// one CTA per chunk: sort the chunk's columns by signature, emit slot->column and per-warp iteration counts
-__global__ void __launch_bounds__(512)
-fp_sort_kernel(const int *__restrict__ chunkptr, const unsigned long long *__restrict__ sig, const long long *__restrict__ adjptr,
-               int *__restrict__ slotcol, int *__restrict__ warpniter)
+// one CTA per chunk of FP_T sorted slots: slot -> column, accumulator offsets, chunk total, rounds per warp
+__global__ void __launch_bounds__(FP_T)
+fp_chunk_kernel(long long ncols, const int *__restrict__ order, const long long *__restrict__ colptr, const long long *__restrict__ adjptr,
+                int *__restrict__ slotcol, int *__restrict__ slotoff, int *__restrict__ chunktot, int *__restrict__ warpniter)
 {
-    __shared__ unsigned long long key[512];
-    __shared__ int val[512];
-    const int chunk = blockIdx.x, k0 = chunkptr[chunk], k1 = chunkptr[chunk + 1];
-    const int nc = k1 - k0, t = threadIdx.x;
-    key[t] = t < nc ? sig[k0 + t] : ~0ull;
-    val[t] = t < nc ? k0 + t : -1;
+    __shared__ int sc[FP_T];
+    const int t = threadIdx.x;
+    const long long slot = (long long)blockIdx.x * FP_T + t;
+    const int c = slot < ncols ? order[slot] : -1;
+    int len = 0, cnt = 0;
+    if (c >= 0) { len = (int)(colptr[c + 1] - colptr[c]); cnt = (int)(adjptr[c + 1] - adjptr[c]); }
+    sc[t] = len;
     __syncthreads();
-    for (int k = 2; k <= 512; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            int ixj = t ^ j;
-            if (ixj > t) {
-                bool asc = ((t & k) == 0);
-                unsigned long long a = key[t], b = key[ixj];
-                int va = val[t], vb = val[ixj];
-                // ties broken by column index to keep the order deterministic
-                bool gt = (a > b) || (a == b && va > vb);
-                if (gt == asc) { key[t] = b; key[ixj] = a; val[t] = vb; val[ixj] = va; }
-            }
-            __syncthreads();
-        }
-    if (t < FP_THREADS) slotcol[(size_t)chunk * FP_THREADS + t] = val[t];
-    __syncthreads();
-    if (t < FP_WARPS) {
-        int m = 0;
-        for (int l = 0; l < 32; ++l) {
-            int c = val[t * 32 + l];
-            if (c >= 0) m = max(m, (int)(adjptr[c + 1] - adjptr[c]));
-        }
-        warpniter[chunk * FP_WARPS + t] = m;
+    for (int o = 1; o < FP_T; o <<= 1) { // inclusive Hillis-Steele scan
+        int v = t >= o ? sc[t - o] : 0;
+        __syncthreads();
+        sc[t] += v;
+        __syncthreads();
     }
+    slotcol[slot] = c;
+    slotoff[slot] = sc[t] - len;
+    if (t == FP_T - 1) chunktot[blockIdx.x] = sc[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o));
+    if ((t & 31) == 0) warpniter[blockIdx.x * FP_W + (t >> 5)] = cnt;
 }
 
 template <typename PosT>
@@ -288,21 +516,18 @@ __global__ void fp_fill_kernel(long long nslots, int ns, int rw, int posstride, 
     long long wg = s >> 5;
     int lane = (int)(s & 31);
     int niter = warpniter[wg];
-    unsigned *out = rec + warpoff[wg] + lane;
+    unsigned *out = rec + warpoff[wg] + lane * rw;
     int k = slotcol[s];
     long long p0 = 0, p1 = 0;
     if (k >= 0) { p0 = adjptr[k]; p1 = adjptr[k + 1]; }
     for (int r = 0; r < niter; ++r) {
-        unsigned w[8] = {0xffffffffu, 0, 0, 0, 0, 0, 0, 0};
+        unsigned w[4] = {0xffffffffu, 0, 0, 0};
         long long p = p0 + r;
         if (p < p1) {
-            w[0] = (unsigned)adjcell[p];
-            unsigned bytes[28];
-            bytes[0] = adjloc[p];
-            for (int t = 0; t < ns; ++t) bytes[1 + t] = (unsigned)posmap[p * posstride + t] & 0xff;
-            for (int b = 0; b < 1 + ns; ++b) w[1 + b / 4] |= bytes[b] << (8 * (b % 4));
+            w[0] = (unsigned)adjcell[p] | ((unsigned)adjloc[p] << FP_CELLBITS);
+            for (int t = 0; t < ns; ++t) w[1 + t / 4] |= ((unsigned)posmap[p * posstride + t] & 0xff) << (8 * (t % 4));
         }
-        for (int j = 0; j < rw; ++j) out[((size_t)r * rw + j) * 32] = w[j];
+        for (int j = 0; j < rw; ++j) out[(size_t)r * 32 * rw + j] = w[j];
     }
 }
 

@@ -66,6 +66,28 @@ def test_fastpath_equals_generic(pkg, ora, engine, dim, order):
             # accumulate on top
             engine.assemble_bilinear(S.pat, desc, accumulate=True, nzval_out=b)
             check_values(b, 2 * ref, what="fast accumulate")
+            # table evaluator (closed form switched off) gives the same sums
+            engine.set_option("fastpath_closed_form", 0)
+            try:
+                engine.assemble_bilinear(S.pat, desc, nzval_out=b)
+            finally:
+                engine.set_option("fastpath_closed_form", 1)
+            check_values(b, ref, what="fast (table evaluator) vs oracle")
+
+
+def test_fastpath_large_unstructured_like(pkg, ora, engine):
+    """Larger perturbed 3D P2 grid: many chunks of every shared-memory class, ragged warps, boundary columns."""
+    X = np.linspace(0, 1, 10)
+    g = pkg.simplexgrid(X ** 1.1, X, X ** 0.9)
+    rng = np.random.default_rng(3)
+    interior = np.all((g.coords > 1e-9) & (g.coords < 1 - 1e-9), axis=1)
+    g.coords[interior] += 0.02 * (rng.random((int(interior.sum()), 3)) - 0.5)
+    g._cache.clear()
+    S = System(pkg, ora, engine, g, [pkg.H1P2(1, 3)])
+    nz = np.empty(S.rowval.size)
+    engine.assemble_bilinear(S.pat, engine.make_opdesc([(0, GRAD)], [(0, GRAD)], factor=2.0), nzval_out=nz)
+    ref = ora.assemble_bilinear(S.omesh, S.oargs([(0, GRAD)]), S.oargs([(0, GRAD)]), factor=2.0, csc=(S.colptr, S.rowval))
+    check_values(nz, ref)
 
 
 @pytest.mark.parametrize("dim,order,kernel,params", [
