@@ -132,15 +132,18 @@ def run_ours(args):
     barrier()
     eng.event_record(0)
     kern_ms = np.zeros(3)
+    rhs_ms = np.zeros(3)
     for _ in range(args.steps):
         eng.assemble_bilinear(pat, lap)
         kern_ms += np.array(eng.last_timings())
         eng.assemble_linear(pat, rhs)
+        rhs_ms += np.array(eng.last_timings())
     eng.event_record(1)
     ms_total = eng.event_elapsed_ms(0, 1)
     barrier()
     clocks = sampler.finish() if sampler else None
     kern_ms /= args.steps
+    rhs_ms /= args.steps
 
     # ---- e2e through the C-ABI with HOST buffers: H2D of the coordinates (pinned), D2H of nzval and b
     coords_h = torch.from_numpy(np.ascontiguousarray(grid.coords)).pin_memory()
@@ -204,6 +207,8 @@ def run_ours(args):
             "clocks": clocks,
             "setup_s": {"mesh_host": t_mesh, "upload_adjacency_pattern": t_setup},
             "checksum_sum_nzval": checksum,
+            "phase_ms": {"stiffness_geo": kern_ms[0], "stiffness_gather": kern_ms[1], "rhs_cell": rhs_ms[0], "rhs_gather": rhs_ms[1]},
+            "plan": eng.plan_stats(pat, 0),
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(pkg, args)

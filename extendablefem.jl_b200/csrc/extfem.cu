@@ -12,6 +12,7 @@
 #include "kernels_generic.cuh"
 #include "pattern.cuh"
 #include "fastpath.cuh"
+#include "fastplan.cuh"
 #include "solver.cuh"
 
 namespace extfem {
@@ -47,8 +48,18 @@ struct FastPlan {
     DevBuf chunklist, slotcol, slotoff, chunktot, warpniter, warpoff, rec;
 };
 
+// template plan of one diagonal block (fastplan.cuh)
+struct TemplatePlan {
+    bool ready = false;
+    GeoLayout Lg{0, 1, 0, 0};
+    int nwarps = 0, nctas = 0, ngroups = 0, ntemplates = 0, pool_bytes = 0;
+    long long nrounds = 0, nleft = 0, ncols = 0;
+    DevBuf ctaw0, wdesc, slotcol, slotpb, tmpl, leftcols;
+};
+
 struct Pattern {
     std::vector<std::unique_ptr<FastPlan>> fastplans; // per column block (diagonal blocks only)
+    std::vector<std::unique_ptr<TemplatePlan>> tplans;
     std::vector<long long> hcolptr;                   // host copy of colptr (plan construction)
     std::vector<int> rowspaces, colspaces;
     std::vector<long long> rowoff, coloff;     // size n+1
@@ -90,8 +101,10 @@ struct Ctx {
     std::map<TableKey, std::unique_ptr<DevTables>> tables;
     std::map<std::pair<int, int>, std::unique_ptr<DevQuad>> quads; // (dim, order)
     DevBuf custom_qw, custom_qx;
-    DevBuf loc, bloc, sol, params_scratch, tab, geo, visit;
+    DevBuf loc, bloc, sol, params_scratch, tab, geo, visit, fq;
     bool fast_enabled = true;   // option "fastpath"
+    bool tmpl_enabled = true;   // option "fastpath_templates": 0 keeps every column on the record kernel
+    int tmpl_mincols = 24;      // option "template_min_cols": smallest group of columns that gets a template
     bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator
     long long launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -505,6 +518,216 @@ static int finish_timing(Ctx *ctx)
     return 0;
 }
 
+// ---- template plan (fastplan.cuh) -------------------------------------------------------------------
+template <typename K, typename V>
+static int radix_sort_pairs(Ctx *ctx, const K *kin, K *kout, const V *vin, V *vout, long long n, int endbit = (int)sizeof(K) * 8)
+{
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, kout, vin, vout, n, 0, endbit, ctx->stream);
+    DevBuf tmp;
+    if (int rc = ensure(ctx, tmp, tb)) return rc;
+    EXTFEM_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, kin, kout, vin, vout, n, 0, endbit, ctx->stream));
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // tmp is freed on return
+    return 0;
+}
+
+static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
+{
+    if (!P.tplans[b]) P.tplans[b] = std::make_unique<TemplatePlan>();
+    TemplatePlan &T = *P.tplans[b];
+    if (T.ready) return 0;
+    T.ready = true;
+    Space &S = *ctx->spaces[P.colspaces[b]];
+    Mesh &M = *ctx->meshes[S.mesh];
+    const long long ncols = S.ndofs;
+    T.ncols = ncols;
+    T.Lg = GeoLayout{0, 1, M.ncells, M.ncells};
+    cudaStream_t st = ctx->stream;
+    auto all_left = [&]() -> int { // no templates: every column goes to the record kernel, geometry stays [cell][NG]
+        T.nwarps = T.nctas = T.ntemplates = 0;
+        T.Lg = GeoLayout{0, 1, M.ncells, M.ncells};
+        if (int rc = ensure(ctx, T.leftcols, (size_t)ncols * 4)) return rc;
+        tp_iota_kernel<<<nblocks(ncols, 256), 256, 0, st>>>(ncols, T.leftcols.as<int>());
+        LAUNCHED(ctx);
+        T.nleft = ncols;
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+        return 0;
+    };
+    if (!ctx->tmpl_enabled || ncols < 64 || ns > 10 || P.poswidth != 1 || M.ncells >= (1ll << 31) - 4096) return all_left();
+    const long long *colptr = P.colptr.as<long long>() + P.coloff[b];
+    const unsigned char *posmap = P.posmap[b]->as<unsigned char>() + P.rowlocoff[b];
+    const int posstride = P.NRpat;
+    const long long *adjptr = S.adjptr.as<long long>();
+    const int *adjcell = S.adjcell.as<int>();
+    const unsigned char *adjloc = S.adjloc.as<unsigned char>();
+    const unsigned gb = nblocks(ncols, 256);
+
+    DevBuf hash, base, col, key, skey, order, flag, gid1, gstart, ok, hist;
+    if (int rc = ensure(ctx, hash, ncols * 8)) return rc;
+    if (int rc = ensure(ctx, base, ncols * 4)) return rc;
+    if (int rc = ensure(ctx, col, ncols * 4)) return rc;
+    if (int rc = ensure(ctx, key, ncols * 8)) return rc;
+    if (int rc = ensure(ctx, skey, ncols * 8)) return rc;
+    if (int rc = ensure(ctx, order, ncols * 4)) return rc;
+    tp_sig_kernel<<<gb, 256, 0, st>>>(ncols, ns, posstride, colptr, adjptr, adjcell, adjloc, posmap, hash.as<unsigned long long>(),
+                                      base.as<int>(), col.as<int>());
+    LAUNCHED(ctx);
+    // period P of the transposed geometry order: most frequent base-cell stride inside a signature class
+    if (int rc = radix_sort_pairs(ctx, hash.as<unsigned long long>(), skey.as<unsigned long long>(), col.as<int>(), order.as<int>(), ncols))
+        return rc;
+    if (int rc = ensure(ctx, hist, 65 * 8)) return rc;
+    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(hist.p, 0, 65 * 8, st));
+    tp_stride_hist_kernel<<<gb, 256, 0, st>>>(ncols, skey.as<unsigned long long>(), order.as<int>(), base.as<int>(),
+                                              hist.as<unsigned long long>());
+    LAUNCHED(ctx);
+    unsigned long long hh[65];
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(hh, hist.p, sizeof(hh), cudaMemcpyDeviceToHost, st));
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    int Pp = 1;
+    for (int d = 1; d <= 64; ++d) if (hh[d] > hh[Pp]) Pp = d;
+    if (hh[Pp] == 0) Pp = 1;
+    GeoLayout Lg;
+    Lg.soa = 1; Lg.P = Pp; Lg.N = (M.ncells + Pp - 1) / Pp; Lg.Npad = Lg.N * Pp;
+    // final signature includes the residue of the base cell modulo P
+    tp_key2_kernel<<<gb, 256, 0, st>>>(ncols, Pp, hash.as<unsigned long long>(), base.as<int>(), key.as<unsigned long long>(), col.as<int>());
+    LAUNCHED(ctx);
+    if (int rc = radix_sort_pairs(ctx, key.as<unsigned long long>(), skey.as<unsigned long long>(), col.as<int>(), order.as<int>(), ncols))
+        return rc;
+    if (int rc = ensure(ctx, flag, ncols * 4)) return rc;
+    if (int rc = ensure(ctx, gid1, ncols * 4)) return rc;
+    tp_flag_kernel<<<gb, 256, 0, st>>>(ncols, skey.as<unsigned long long>(), flag.as<int>());
+    LAUNCHED(ctx);
+    {
+        size_t tb = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, tb, flag.as<int>(), gid1.as<int>(), ncols, st);
+        DevBuf tmp;
+        if (int rc = ensure(ctx, tmp, tb)) return rc;
+        EXTFEM_CUDA_CHECK(ctx, cub::DeviceScan::InclusiveSum(tmp.p, tb, flag.as<int>(), gid1.as<int>(), ncols, st));
+        LAUNCHED(ctx);
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    }
+    int ngroups = 0;
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(&ngroups, gid1.as<int>() + (ncols - 1), 4, cudaMemcpyDeviceToHost));
+    T.ngroups = ngroups;
+    if (int rc = ensure(ctx, gstart, ((size_t)ngroups + 1) * 4)) return rc;
+    tp_gstart_kernel<<<gb, 256, 0, st>>>(ncols, flag.as<int>(), gid1.as<int>(), gstart.as<int>());
+    LAUNCHED(ctx);
+    if (int rc = ensure(ctx, ok, ncols)) return rc;
+    tp_verify_kernel<<<gb, 256, 0, st>>>(ncols, ns, posstride, Pp, order.as<int>(), gid1.as<int>(), gstart.as<int>(), colptr, adjptr,
+                                         adjcell, adjloc, posmap, ok.as<unsigned char>());
+    LAUNCHED(ctx);
+    DevBuf gnw, gw0, gnr, gr0;
+    if (int rc = ensure(ctx, gnw, ((size_t)ngroups + 1) * 4)) return rc;
+    if (int rc = ensure(ctx, gw0, ((size_t)ngroups + 1) * 4)) return rc;
+    if (int rc = ensure(ctx, gnr, ((size_t)ngroups + 1) * 8)) return rc;
+    if (int rc = ensure(ctx, gr0, ((size_t)ngroups + 1) * 8)) return rc;
+    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(gnw.p, 0, ((size_t)ngroups + 1) * 4, st));
+    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(gnr.p, 0, ((size_t)ngroups + 1) * 8, st));
+    tp_group_kernel<<<nblocks(ngroups, 256), 256, 0, st>>>(ngroups, ctx->tmpl_mincols, gstart.as<int>(), order.as<int>(), adjptr,
+                                                           gnw.as<int>(), gnr.as<long long>());
+    LAUNCHED(ctx);
+    {
+        size_t tb1 = 0, tb2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb1, gnw.as<int>(), gw0.as<int>(), ngroups + 1, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb2, gnr.as<long long>(), gr0.as<long long>(), ngroups + 1, st);
+        DevBuf tmp;
+        if (int rc = ensure(ctx, tmp, std::max(tb1, tb2))) return rc;
+        EXTFEM_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tb1, gnw.as<int>(), gw0.as<int>(), ngroups + 1, st));
+        EXTFEM_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tb2, gnr.as<long long>(), gr0.as<long long>(), ngroups + 1, st));
+        LAUNCHED(ctx); LAUNCHED(ctx);
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    }
+    int nwarps = 0;
+    long long nrounds = 0;
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(&nwarps, gw0.as<int>() + ngroups, 4, cudaMemcpyDeviceToHost));
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(&nrounds, gr0.as<long long>() + ngroups, 8, cudaMemcpyDeviceToHost));
+    if (nwarps == 0 || nrounds >= (1ll << 31) - 1) return all_left();
+
+    // slots, warp descriptors (template order), leftover columns
+    DevBuf wd0, wkey, wkey2, widx, widx2, left, leftsel, nsel;
+    if (int rc = ensure(ctx, T.tmpl, (size_t)nrounds * TP_TW * 4)) return rc;
+    if (int rc = ensure(ctx, T.slotcol, (size_t)nwarps * 32 * 4)) return rc;
+    if (int rc = ensure(ctx, T.slotpb, (size_t)nwarps * 32 * 4)) return rc;
+    if (int rc = ensure(ctx, wd0, (size_t)nwarps * 16)) return rc;
+    if (int rc = ensure(ctx, wkey, (size_t)nwarps * 4)) return rc;
+    if (int rc = ensure(ctx, wkey2, (size_t)nwarps * 4)) return rc;
+    if (int rc = ensure(ctx, widx, (size_t)nwarps * 4)) return rc;
+    if (int rc = ensure(ctx, widx2, (size_t)nwarps * 4)) return rc;
+    if (int rc = ensure(ctx, left, ncols)) return rc;
+    if (int rc = ensure(ctx, leftsel, ncols * 4)) return rc;
+    if (int rc = ensure(ctx, nsel, 8)) return rc;
+    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(T.slotcol.p, 0xff, (size_t)nwarps * 32 * 4, st));
+    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(T.slotpb.p, 0, (size_t)nwarps * 32 * 4, st));
+    tp_tmpl_kernel<<<nblocks(ngroups, 128), 128, 0, st>>>(ngroups, ns, posstride, Lg, gstart.as<int>(), order.as<int>(), gnr.as<long long>(),
+                                                          gr0.as<long long>(), adjptr, adjcell, adjloc, posmap, T.tmpl.as<unsigned>());
+    LAUNCHED(ctx);
+    tp_slot_kernel<<<gb, 256, 0, st>>>(ncols, Lg, order.as<int>(), gid1.as<int>(), gstart.as<int>(), gnw.as<int>(), gw0.as<int>(),
+                                       gnr.as<long long>(), gr0.as<long long>(), ok.as<unsigned char>(), base.as<int>(), colptr,
+                                       T.slotcol.as<int>(), T.slotpb.as<int>(), wd0.as<int4>(), wkey.as<unsigned>(), widx.as<int>(),
+                                       left.as<unsigned char>());
+    LAUNCHED(ctx);
+    {
+        size_t tb = 0;
+        cub::DeviceSelect::Flagged(nullptr, tb, order.as<int>(), left.as<unsigned char>(), leftsel.as<int>(), nsel.as<long long>(), ncols, st);
+        DevBuf tmp;
+        if (int rc = ensure(ctx, tmp, tb)) return rc;
+        EXTFEM_CUDA_CHECK(ctx, cub::DeviceSelect::Flagged(tmp.p, tb, order.as<int>(), left.as<unsigned char>(), leftsel.as<int>(),
+                                                          nsel.as<long long>(), ncols, st));
+        LAUNCHED(ctx);
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    }
+    long long nleft = 0;
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(&nleft, nsel.p, 8, cudaMemcpyDeviceToHost));
+    if (ncols - nleft < ncols / 2) return all_left(); // templates cover less than half of the columns: not worth the layout
+    T.nleft = nleft;
+    if (int rc = ensure(ctx, T.leftcols, (size_t)std::max(nleft, 1ll) * 4)) return rc;
+    if (nleft > 0) {
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tb, leftsel.as<int>(), T.leftcols.as<int>(), nleft, 0, 32, st);
+        DevBuf tmp;
+        if (int rc = ensure(ctx, tmp, tb)) return rc;
+        EXTFEM_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortKeys(tmp.p, tb, leftsel.as<int>(), T.leftcols.as<int>(), nleft, 0, 32, st));
+        LAUNCHED(ctx);
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    }
+    // launch order: warps sorted by the first adjacent cell of their first column, so that all templates sweep the
+    // mesh together (geometry is read from DRAM once, output streams advance sequentially)
+    if (int rc = radix_sort_pairs(ctx, wkey.as<unsigned>(), wkey2.as<unsigned>(), widx.as<int>(), widx2.as<int>(), nwarps)) return rc;
+    std::vector<int4> hw((size_t)nwarps), launch((size_t)nwarps);
+    std::vector<int> hidx((size_t)nwarps), ctaw0;
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hw.data(), wd0.p, (size_t)nwarps * 16, cudaMemcpyDeviceToHost));
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hidx.data(), widx2.p, (size_t)nwarps * 4, cudaMemcpyDeviceToHost));
+    int pool = TP_POOL_BYTES / 8;
+    for (int w = 0; w < nwarps; ++w) pool = std::max(pool, (hw[w].y >> 16) * TP_LD);
+    int cur_w = 0, cur_s = 0;
+    ctaw0.push_back(0);
+    for (int i = 0; i < nwarps; ++i) {
+        const int4 d = hw[hidx[i]];
+        const int need = (d.y >> 16) * TP_LD;
+        if (cur_w == TP_MAXW || cur_s + need > pool) { ctaw0.push_back(i); cur_w = 0; cur_s = 0; }
+        launch[i] = make_int4(d.x, d.y, d.z, cur_s);
+        cur_s += need; ++cur_w;
+    }
+    ctaw0.push_back(nwarps);
+    T.nctas = (int)ctaw0.size() - 1;
+    T.nwarps = nwarps;
+    T.nrounds = nrounds;
+    T.pool_bytes = pool * 8;
+    T.Lg = Lg;
+    {
+        std::vector<int> hnw((size_t)ngroups);
+        EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hnw.data(), gnw.p, (size_t)ngroups * 4, cudaMemcpyDeviceToHost));
+        T.ntemplates = 0;
+        for (int g = 0; g < ngroups; ++g) T.ntemplates += hnw[g] > 0;
+    }
+    if (int rc = upload(ctx, T.wdesc, launch.data(), launch.size() * 16)) return rc;
+    if (int rc = upload(ctx, T.ctaw0, ctaw0.data(), ctaw0.size() * 4)) return rc;
+    EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
 // ---- fast path (fastpath.cuh) --------------------------------------------------------------------
 // Plan of one diagonal block: columns sorted by adjacency signature inside windows, cut into chunks of FP_T
 // slots, chunks ordered by shared-memory class; lane-contiguous records per warp round.
@@ -516,8 +739,11 @@ static int build_fast_plan(Ctx *ctx, Pattern &P, int b, int ns)
     F.ready = true;
     Space &S = *ctx->spaces[P.colspaces[b]];
     Mesh &M = *ctx->meshes[S.mesh];
-    if (M.ncells >= (1ll << FP_CELLBITS) || ns > (1 << FP_KLBITS)) return 0; // record word 0 cannot hold cell | kl
-    const long long ncols = S.ndofs;
+    if (M.ncells + 64 >= (1ll << FP_CELLBITS) || ns > (1 << FP_KLBITS)) return 0; // record word 0 cannot hold cell | kl
+    if (int rc = build_template_plan(ctx, P, b, ns)) return rc;
+    TemplatePlan &T = *P.tplans[b];
+    const long long ncols = T.nleft;            // the record kernel owns the columns without a template
+    if (ncols == 0) { F.nchunks = 0; F.usable = true; return 0; }
     const long long *colptr = P.colptr.as<long long>() + P.coloff[b];
     F.nchunks = (int)((ncols + FP_T - 1) / FP_T);
     const long long nslots = (long long)F.nchunks * FP_T;
@@ -527,8 +753,8 @@ static int build_fast_plan(Ctx *ctx, Pattern &P, int b, int ns)
         if (int rc = ensure(ctx, key2, ncols * 8)) return rc;
         if (int rc = ensure(ctx, col, ncols * 4)) return rc;
         if (int rc = ensure(ctx, order, ncols * 4)) return rc;
-        fp_key_kernel<<<nblocks(ncols, 256), 256, 0, ctx->stream>>>(ncols, S.adjptr.as<long long>(), S.adjloc.as<unsigned char>(),
-                                                                   key.as<unsigned long long>(), col.as<int>());
+        fp_key_kernel<<<nblocks(ncols, 256), 256, 0, ctx->stream>>>(ncols, T.leftcols.as<int>(), S.adjptr.as<long long>(),
+                                                                   S.adjloc.as<unsigned char>(), key.as<unsigned long long>(), col.as<int>());
         LAUNCHED(ctx);
         size_t tb = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tb, key.as<unsigned long long>(), key2.as<unsigned long long>(), col.as<int>(),
@@ -574,7 +800,7 @@ static int build_fast_plan(Ctx *ctx, Pattern &P, int b, int ns)
     if (int rc = ensure(ctx, F.rec, (size_t)tot * 4 + 16)) return rc;
     fp_fill_kernel<unsigned char><<<nblocks(nslots, 256), 256, 0, ctx->stream>>>(
         nslots, ns, rw, P.NRpat, F.slotcol.as<int>(), F.warpniter.as<int>(), F.warpoff.as<long long>(), S.adjptr.as<long long>(),
-        S.adjcell.as<int>(), S.adjloc.as<unsigned char>(), P.posmap[b]->as<unsigned char>() + P.rowlocoff[b], F.rec.as<unsigned>());
+        S.adjcell.as<int>(), S.adjloc.as<unsigned char>(), P.posmap[b]->as<unsigned char>() + P.rowlocoff[b], F.rec.as<unsigned>(), T.Lg);
     LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
     EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -582,53 +808,89 @@ static int build_fast_plan(Ctx *ctx, Pattern &P, int b, int ns)
     return 0;
 }
 
-template <int DIM, int GEO, class EV>
-static int launch_fast(Ctx *ctx, Pattern &P, FastPlan &F, int b, const Prepared &R, const extfem_opdesc *d, double geoscale,
-                       int accumulate)
+template <class EV, bool FIRST>
+static int launch_template(Ctx *ctx, Pattern &P, TemplatePlan &T, int b, int accumulate)
+{
+    TPArgs A;
+    A.ctaw0 = T.ctaw0.as<int>(); A.wdesc = T.wdesc.as<int4>(); A.slotcol = T.slotcol.as<int>(); A.slotpb = T.slotpb.as<int>();
+    A.tmpl = T.tmpl.as<unsigned>(); A.colptr = P.colptr.as<long long>() + P.coloff[b]; A.nzval = P.nzval.as<double>();
+    A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
+    auto k = tp_gather_kernel<EV, FIRST>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    k<<<T.nctas, TP_MAXW * 32, T.pool_bytes, ctx->stream>>>(A);
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+template <int DIM, int GEO, class EV, bool SOA>
+static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T, int b, const Prepared &R, const extfem_opdesc *d,
+                              double geoscale, int accumulate)
 {
     constexpr int NG = fp_ng(DIM, GEO);
     static_assert(NG == EV::NG, "geometry record / evaluator mismatch");
     Mesh &M = *R.mesh;
-    if (int rc = ensure(ctx, ctx->geo, (size_t)M.ncells * NG * 8)) return rc;
+    if (int rc = ensure(ctx, ctx->geo, (size_t)(SOA ? T.Lg.Npad : M.ncells) * NG * 8)) return rc;
     if (d->nregions > 0) if (int rc = upload(ctx, ctx->visit, d->regions, (size_t)d->nregions * 4)) return rc;
-    fp_geo_kernel<DIM, GEO><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(
+    fp_geo_kernel<DIM, GEO, SOA><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(
         M.ncells, M.coords.as<double>(), M.cellnodes.as<int>(), M.regions.as<int>(), M.vol.as<double>(), d->factor * geoscale,
-        d->nregions, ctx->visit.as<int>(), ctx->geo.as<double>());
+        d->nregions, ctx->visit.as<int>(), ctx->geo.as<double>(), T.Lg);
     LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    FastArgs A;
-    A.plan.chunklist = F.chunklist.as<int>(); A.plan.slotcol = F.slotcol.as<int>(); A.plan.slotoff = F.slotoff.as<int>();
-    A.plan.chunktot = F.chunktot.as<int>();
-    A.plan.warpniter = F.warpniter.as<int>(); A.plan.warpoff = F.warpoff.as<long long>(); A.plan.rec = F.rec.as<unsigned>();
-    A.colptr = P.colptr.as<long long>() + P.coloff[b];
-    A.nzval = P.nzval.as<double>(); A.geo = ctx->geo.as<double>(); A.overwrite = !accumulate;
-    // One launch per shared-memory class.  The small class runs one warp group per chunk; the larger classes are
-    // limited by shared memory, so their local rows are split over two warp groups (vertex rows | other rows) when
-    // the element has both (EV::NS > EV::NV).
-    constexpr int NGRP_BIG = EV::NS > EV::NV ? 2 : 1;
-    auto k0 = fp_gather_kernel<EV, 1, 6>;
-    auto k1 = fp_gather_kernel<EV, NGRP_BIG, (NGRP_BIG == 2 ? 3 : 4)>;
-    auto k2 = fp_gather_kernel<EV, NGRP_BIG, (NGRP_BIG == 2 ? 3 : 3)>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
-        EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
-        EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
-        attr_set = true;
+    if (SOA && T.nwarps > 0) {
+        // first-touch stores need: overwrite, and column segments that hold rows of this block only
+        const bool first = !accumulate && P.rowspaces.size() == 1;
+        if (int rc = first ? launch_template<EV, true>(ctx, P, T, b, accumulate) : launch_template<EV, false>(ctx, P, T, b, accumulate))
+            return rc;
     }
-    for (int c = FP_NCLASS - 1; c >= 0; --c) { // longest-running class first
-        int n = F.cls_start[c + 1] - F.cls_start[c];
-        if (n == 0) continue;
-        A.chunk0 = F.cls_start[c];
-        const size_t smem = (size_t)F.cls_maxtot[c] * 8; // what the class actually needs
-        if (c == 0) k0<<<n, FP_T, smem, ctx->stream>>>(A);
-        else if (c == 1) k1<<<n, FP_T * NGRP_BIG, smem, ctx->stream>>>(A);
-        else k2<<<n, FP_T * NGRP_BIG, smem, ctx->stream>>>(A);
-        LAUNCHED(ctx);
+    if (F.nchunks > 0) {
+        FastArgs A;
+        A.plan.chunklist = F.chunklist.as<int>(); A.plan.slotcol = F.slotcol.as<int>(); A.plan.slotoff = F.slotoff.as<int>();
+        A.plan.chunktot = F.chunktot.as<int>();
+        A.plan.warpniter = F.warpniter.as<int>(); A.plan.warpoff = F.warpoff.as<long long>(); A.plan.rec = F.rec.as<unsigned>();
+        A.colptr = P.colptr.as<long long>() + P.coloff[b];
+        A.nzval = P.nzval.as<double>(); A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
+        // One launch per shared-memory class.  The small class runs one warp group per chunk; the larger classes are
+        // limited by shared memory, so their local rows are split over two warp groups (vertex rows | other rows) when
+        // the element has both (EV::NS > EV::NV).
+        constexpr int NGRP_BIG = EV::NS > EV::NV ? 2 : 1;
+        auto k0 = fp_gather_kernel<EV, 1, 6, SOA>;
+        auto k1 = fp_gather_kernel<EV, NGRP_BIG, (NGRP_BIG == 2 ? 3 : 4), SOA>;
+        auto k2 = fp_gather_kernel<EV, NGRP_BIG, 3, SOA>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
+            EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
+            EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
+            attr_set = true;
+        }
+        for (int c = FP_NCLASS - 1; c >= 0; --c) { // longest-running class first
+            int n = F.cls_start[c + 1] - F.cls_start[c];
+            if (n == 0) continue;
+            A.chunk0 = F.cls_start[c];
+            const size_t smem = (size_t)F.cls_maxtot[c] * 8; // what the class actually needs
+            if (c == 0) k0<<<n, FP_T, smem, ctx->stream>>>(A);
+            else if (c == 1) k1<<<n, FP_T * NGRP_BIG, smem, ctx->stream>>>(A);
+            else k2<<<n, FP_T * NGRP_BIG, smem, ctx->stream>>>(A);
+            LAUNCHED(ctx);
+        }
     }
     EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     return 0;
+}
+
+template <int DIM, int GEO, class EV>
+static int launch_fast(Ctx *ctx, Pattern &P, FastPlan &F, int b, const Prepared &R, const extfem_opdesc *d, double geoscale,
+                       int accumulate)
+{
+    TemplatePlan &T = *P.tplans[b];
+    return T.Lg.soa ? launch_fast_layout<DIM, GEO, EV, true>(ctx, P, F, T, b, R, d, geoscale, accumulate)
+                    : launch_fast_layout<DIM, GEO, EV, false>(ctx, P, F, T, b, R, d, geoscale, accumulate);
 }
 
 // reference tables S[kl][t][g] of the table evaluator, from the SAME quadrature rule / basis as the generic path
@@ -761,6 +1023,76 @@ static int try_fast_bilinear(Ctx *ctx, Pattern &P, const Prepared &R, const extf
     return 0;
 }
 
+// fast right-hand side: LinearOperator(f, [id(u)]) on a scalar P1/P2 space (linear_operator.jl:584-640).  Per cell the
+// point values factor*w_q*|T|*f(x_q) (structure-of-arrays, geometry order), per dof an owner-computes sum over the
+// adjacent cells driven by the template plan of the block.
+static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem_opdesc *d, int accumulate, bool *fast)
+{
+    *fast = false;
+    if (!ctx->fast_enabled) return 0;
+    const OpDev &op = R.op;
+    if (d->ntest != 1 || d->nargs != 0 || d->test_op[0] != EXTFEM_OP_ID || op.nout != 1 || op.nq > TP_NQMAX) return 0;
+    const int b = d->test_block[0];
+    if (!P.square || b >= (int)P.colspaces.size() || P.poswidth != 1 || !P.coupling[(size_t)b * P.rowspaces.size() + b]) return 0;
+    Space &S = *ctx->spaces[P.rowspaces[b]];
+    if (S.ncomp != 1 || S.nscalar > 10) return 0;
+    Mesh &M = *R.mesh;
+    const int dim = op.dim, ns = S.nscalar;
+    if (int rc = build_template_plan(ctx, P, b, ns)) return rc;
+    TemplatePlan &T = *P.tplans[b];
+    // reference basis values at the operator's quadrature points
+    QuadRule Q;
+    Q.dim = dim; Q.nq = op.nq;
+    Q.w.resize(op.nq); Q.x.resize((size_t)op.nq * dim);
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.w.data(), op.qw, op.nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.x.data(), op.qx, (size_t)op.nq * dim * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<double> v, g, phi((size_t)10 * TP_NQMAX, 0.0);
+    ref_basis(S.order, dim, Q, v, g);
+    for (int q = 0; q < op.nq; ++q)
+        for (int kl = 0; kl < ns; ++kl) phi[(size_t)kl * TP_NQMAX + q] = v[(size_t)q * ns + kl];
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_phi, phi.data(), phi.size() * 8, 0, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = ensure(ctx, ctx->fq, (size_t)T.Lg.Npad * op.nq * 8)) return rc;
+    double *bblk = P.b.as<double>() + P.rowoff[b];
+    if (!accumulate && P.rowspaces.size() > 1) {
+        for (size_t r = 0; r < P.rowspaces.size(); ++r) {
+            if ((int)r == b) continue;
+            EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(P.b.as<double>() + P.rowoff[r], 0, (size_t)(P.rowoff[r + 1] - P.rowoff[r]) * 8, ctx->stream));
+        }
+    }
+    RhsCellArgs C;
+    memset(&C, 0, sizeof(C));
+    C.ncells = M.ncells; C.coords = M.coords.as<double>(); C.cellnodes = M.cellnodes.as<int>(); C.regions = M.regions.as<int>();
+    C.vol = M.vol.as<double>(); C.qw = op.qw; C.qx = op.qx; C.tabulated = op.tabulated; C.nq = op.nq; C.kernel_id = op.kernel_id;
+    C.nregions = op.nregions;
+    for (int i = 0; i < op.nregions; ++i) C.visit[i] = op.regions[i];
+    for (int i = 0; i < op.nparams; ++i) C.params[i] = op.params[i];
+    C.factor = op.factor; C.Lg = T.Lg; C.fq = ctx->fq.as<double>();
+    if (dim == 1) tp_rhs_cell_kernel<1><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(C);
+    else if (dim == 2) tp_rhs_cell_kernel<2><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(C);
+    else tp_rhs_cell_kernel<3><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(C);
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (T.nwarps > 0) {
+        TPRhsArgs A;
+        A.nwarps = T.nwarps; A.wdesc = T.wdesc.as<int4>(); A.slotcol = T.slotcol.as<int>(); A.slotpb = T.slotpb.as<int>();
+        A.tmpl = T.tmpl.as<unsigned>(); A.fq = ctx->fq.as<double>(); A.Npad = T.Lg.Npad; A.nq = op.nq; A.b = bblk; A.overwrite = !accumulate;
+        tp_rhs_kernel<<<nblocks(T.nwarps, 8), 256, 0, ctx->stream>>>(A);
+        LAUNCHED(ctx);
+    }
+    if (T.nleft > 0) {
+        RhsLeftArgs A;
+        A.nleft = T.nleft; A.leftcols = T.leftcols.as<int>(); A.adjptr = S.adjptr.as<long long>(); A.adjcell = S.adjcell.as<int>();
+        A.adjloc = S.adjloc.as<unsigned char>(); A.fq = ctx->fq.as<double>(); A.Lg = T.Lg; A.nq = op.nq; A.b = bblk; A.overwrite = !accumulate;
+        tp_rhs_left_kernel<<<nblocks(T.nleft, 256), 256, 0, ctx->stream>>>(A);
+        LAUNCHED(ctx);
+    }
+    EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+    EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    *fast = true;
+    return 0;
+}
+
 } // namespace extfem
 
 using namespace extfem;
@@ -847,6 +1179,8 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     CTX_GUARD(ctx);
     if (key && !strcmp(key, "fastpath")) { C->fast_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_closed_form")) { C->bary_enabled = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_min_cols")) { C->tmpl_mincols = value < 1 ? 1 : value; return EXTFEM_OK; }
     return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("unknown option ") + (key ? key : "(null)"));
 }
 
@@ -1080,6 +1414,7 @@ int extfem_pattern_build(extfem_ctx *ctx, int nrow, const int *rowspaces, int nc
     P.nchunks = (int)chunks.size() - 1;
     P.hcolptr = std::move(hcolptr);
     P.fastplans.resize(ncol);
+    P.tplans.resize(ncol);
     if (int rc = upload(C, P.chunkptr, chunks.data(), chunks.size() * 4)) return rc;
     EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
     C->patterns.push_back(std::move(Pp));
@@ -1150,22 +1485,42 @@ int extfem_assemble_linear(extfem_ctx *ctx, int pattern, const extfem_opdesc *d,
     Prepared R;
     if (int rc = prepare(C, P, d, KIND_LINEAR, d && d->nargs > 0 ? sol : nullptr, R)) return rc;
     const OpDev &op = R.op;
-    if (int rc = ensure(C, C->bloc, (size_t)op.ncells * op.NR * 8)) return rc;
     EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[0], C->stream));
-    int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
-        constexpr int DIM = decltype(dimc)::value;
-        size_t per_cell = sizeof(CellGeo<DIM>) + (size_t)op.nq * op.nout * 8;
-        int cpb = cells_per_block(per_cell);
-        local_linear_kernel<DIM><<<nblocks(op.ncells, cpb), 256, cpb * per_cell, C->stream>>>(op, C->bloc.as<double>(), cpb);
-    });
-    if (rcd) return rcd;
-    LAUNCHED(C);
-    EXTFEM_CUDA_CHECK(C, cudaGetLastError());
-    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[1], C->stream));
-    if (int rc = gather_vector(C, P, R, accumulate)) return rc;
-    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[2], C->stream));
+    bool fast = false;
+    if (int rc = try_fast_linear(C, P, R, d, accumulate, &fast)) return rc;
+    if (!fast) {
+        if (int rc = ensure(C, C->bloc, (size_t)op.ncells * op.NR * 8)) return rc;
+        int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
+            constexpr int DIM = decltype(dimc)::value;
+            size_t per_cell = sizeof(CellGeo<DIM>) + (size_t)op.nq * op.nout * 8;
+            int cpb = cells_per_block(per_cell);
+            local_linear_kernel<DIM><<<nblocks(op.ncells, cpb), 256, cpb * per_cell, C->stream>>>(op, C->bloc.as<double>(), cpb);
+        });
+        if (rcd) return rcd;
+        LAUNCHED(C);
+        EXTFEM_CUDA_CHECK(C, cudaGetLastError());
+        EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[1], C->stream));
+        if (int rc = gather_vector(C, P, R, accumulate)) return rc;
+        EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[2], C->stream));
+    }
     if (b_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b_out, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
     return finish_timing(C);
+}
+
+/* statistics of the fast-path plans of column block `block` (built on first use):
+ * [0] period P of the geometry order, [1] templates, [2] template warps, [3] columns on the record kernel,
+ * [4] CTAs of the template kernel, [5] shared-memory pool bytes, [6] template rounds, [7] columns of the block */
+int extfem_plan_stats(extfem_ctx *ctx, int pattern, int block, int64_t *stats8)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (block < 0 || block >= (int)P.tplans.size() || !stats8) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_plan_stats: bad argument");
+    for (int i = 0; i < 8; ++i) stats8[i] = 0;
+    if (!P.tplans[block] || !P.tplans[block]->ready) return EXTFEM_OK;
+    TemplatePlan &T = *P.tplans[block];
+    stats8[0] = T.Lg.P; stats8[1] = T.ntemplates; stats8[2] = T.nwarps; stats8[3] = T.nleft; stats8[4] = T.nctas;
+    stats8[5] = T.pool_bytes; stats8[6] = T.nrounds; stats8[7] = T.ncols;
+    return EXTFEM_OK;
 }
 
 int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc *d, const double *sol, int accumulate,

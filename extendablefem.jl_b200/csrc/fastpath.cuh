@@ -32,6 +32,18 @@
 
 namespace extfem {
 
+// layout of the per-cell scratch records (geometry, RHS point values)
+struct GeoLayout {
+    int soa;            // 0: array of structures [cell][NG]; 1: [g][Npad] in period-P transposed cell order
+    int P;              // period (1: identity)
+    long long N, Npad;  // N = ceil(ncells / P), Npad = N * P
+};
+
+__host__ __device__ __forceinline__ long long geo_perm(const GeoLayout &Lg, long long c)
+{
+    return Lg.P == 1 ? c : (c % Lg.P) * Lg.N + c / Lg.P;
+}
+
 template <int DIM>
 __global__ void cell_volumes_kernel(long long ncells, const double *__restrict__ coords, const int *__restrict__ cellnodes,
                                     double *__restrict__ vol)
@@ -163,11 +175,11 @@ __host__ __device__ __forceinline__ void fp_bary_expand(const double (&G)[DIM * 
 //   FP_GEO_METRIC  f |T| J^-1 J^-T (upper triangle)      table Laplace
 //   FP_GEO_VOLUME  f |T|                                 mass
 //   FP_GEO_BARY    s f |T| grad(l_a).grad(l_b), a<b      closed-form Laplace (s = fp_bary_scale)
-template <int DIM, int GEO>
+template <int DIM, int GEO, bool SOA>
 __global__ void __launch_bounds__(256)
 fp_geo_kernel(long long ncells, const double *__restrict__ coords, const int *__restrict__ cellnodes,
               const int *__restrict__ regions, const double *__restrict__ vol, double factor, int nregions,
-              const int *__restrict__ visit /* device copy of regions list */, double *__restrict__ geo)
+              const int *__restrict__ visit /* device copy of regions list */, double *__restrict__ geo, const GeoLayout Lg)
 {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
@@ -178,7 +190,7 @@ fp_geo_kernel(long long ncells, const double *__restrict__ coords, const int *__
         for (int k = 0; k < nregions; ++k) vis |= (visit[k] == reg);
         if (!vis) f = 0.0;
     }
-    double *g = geo + c * NG;
+    double *g = SOA ? geo + geo_perm(Lg, c) : geo + c * NG;
     if (GEO == FP_GEO_VOLUME) { g[0] = f; return; }
     int cn[DIM + 1];
     if (DIM == 3) {
@@ -248,7 +260,10 @@ fp_geo_kernel(long long ncells, const double *__restrict__ coords, const int *__
                 out[fp_pair_index<DIM>(a, b)] = f * s;   // f already contains fp_bary_scale (host)
             }
     }
-    if (NG % 2 == 0) {
+    if (SOA) {
+#pragma unroll
+        for (int o = 0; o < NG; ++o) g[(size_t)o * Lg.Npad] = out[o];
+    } else if (NG % 2 == 0) {
 #pragma unroll
         for (int o = 0; o < NG; o += 2) reinterpret_cast<double2 *>(g)[o / 2] = make_double2(out[o], out[(o + 1) % NG]);
     } else {
@@ -273,6 +288,7 @@ struct FastArgs {
     const long long *colptr;      // of the column block
     double *nzval;
     const double *geo;
+    long long Npad;               // structure-of-arrays geometry: plane stride
     int overwrite;
     int chunk0;                   // first entry of chunklist of this launch (class)
 };
@@ -361,9 +377,14 @@ __device__ __forceinline__ void fp_load_rec(const unsigned *p, unsigned (&w)[RW]
     }
 }
 
-template <int NG>
-__device__ __forceinline__ void fp_load_geo(const double *__restrict__ geo, int cell, double (&G)[NG])
+template <int NG, bool SOA>
+__device__ __forceinline__ void fp_load_geo(const double *__restrict__ geo, long long Npad, int cell, double (&G)[NG])
 {
+    if (SOA) { // `cell` is the transposed index (stored in the record)
+#pragma unroll
+        for (int g = 0; g < NG; ++g) G[g] = __ldg(geo + (size_t)g * Npad + cell);
+        return;
+    }
     const double *gp = geo + (size_t)cell * NG;
     if (NG % 2 == 0) {
 #pragma unroll
@@ -379,8 +400,9 @@ __device__ __forceinline__ void fp_load_geo(const double *__restrict__ geo, int 
 
 // rounds of one warp over local rows [T0, T1): software pipeline with word 0 (cell | kl) two rounds ahead -- which
 // also pulls the record's line into L1 --, full record and geometry one round ahead, double-buffered by parity
-template <class EV, int T0, int T1>
-__device__ __forceinline__ void fp_rounds(const unsigned *__restrict__ rec, int niter, const double *__restrict__ geo, double *__restrict__ a)
+template <class EV, int T0, int T1, bool SOA>
+__device__ __forceinline__ void fp_rounds(const unsigned *__restrict__ rec, int niter, const double *__restrict__ geo, long long Npad,
+                                          double *__restrict__ a)
 {
     constexpr int NG = EV::NG, RW = fp_rw(EV::NS);
     constexpr unsigned CELLMASK = (1u << FP_CELLBITS) - 1u, NONE = 0xffffffffu;
@@ -389,14 +411,14 @@ __device__ __forceinline__ void fp_rounds(const unsigned *__restrict__ rec, int 
     unsigned c1 = NONE; // word 0 of round r+1
     if (niter > 0) {
         fp_load_rec<RW>(rec, w[0]);
-        if (w[0][0] != NONE) fp_load_geo<NG>(geo, w[0][0] & CELLMASK, G[0]);
+        if (w[0][0] != NONE) fp_load_geo<NG, SOA>(geo, Npad, w[0][0] & CELLMASK, G[0]);
     }
     if (niter > 1) c1 = __ldcs(rec + (size_t)32 * RW);
 #define FP_ROUND(CUR, NXT)                                                                                  \
     {                                                                                                       \
         unsigned c2 = NONE;                                                                                 \
         if (r + 1 < niter) {                                                                                \
-            if (c1 != NONE) fp_load_geo<NG>(geo, c1 & CELLMASK, G[NXT]);                                    \
+            if (c1 != NONE) fp_load_geo<NG, SOA>(geo, Npad, c1 & CELLMASK, G[NXT]);                                    \
             fp_load_rec<RW>(rec + (size_t)(r + 1) * 32 * RW, w[NXT]);                                       \
             if (r + 2 < niter) c2 = __ldcs(rec + (size_t)(r + 2) * 32 * RW);                                \
         }                                                                                                   \
@@ -416,7 +438,7 @@ __device__ __forceinline__ void fp_rounds(const unsigned *__restrict__ rec, int 
 
 // NGRP == 2: warp group 0 accumulates the vertex rows [0, NV), group 1 the remaining rows [NV, NS) of the same
 // columns; the two groups touch disjoint global rows, hence disjoint accumulators, and need no synchronisation.
-template <class EV, int NGRP, int MINB>
+template <class EV, int NGRP, int MINB, bool SOA>
 __global__ void __launch_bounds__(FP_T * NGRP, MINB)
 fp_gather_kernel(const __grid_constant__ FastArgs A)
 {
@@ -451,9 +473,9 @@ fp_gather_kernel(const __grid_constant__ FastArgs A)
     const int niter = A.plan.warpniter[chunk * FP_W + warp];
     const unsigned *rec = A.plan.rec + A.plan.warpoff[chunk * FP_W + warp] + lane * RW;
     double *a = acc + off;
-    if (NGRP == 1) fp_rounds<EV, 0, NS>(rec, niter, A.geo, a);
-    else if (grp == 0) fp_rounds<EV, 0, EV::NV>(rec, niter, A.geo, a);
-    else fp_rounds<EV, EV::NV, NS>(rec, niter, A.geo, a);
+    if (NGRP == 1) fp_rounds<EV, 0, NS, SOA>(rec, niter, A.geo, A.Npad, a);
+    else if (grp == 0) fp_rounds<EV, 0, EV::NV, SOA>(rec, niter, A.geo, A.Npad, a);
+    else fp_rounds<EV, EV::NV, NS, SOA>(rec, niter, A.geo, A.Npad, a);
     __syncthreads();
     for (int s = threadIdx.x >> 5; s < FP_T; s += NT / 32) {
         const long long c0 = s_cp[s];
@@ -465,17 +487,19 @@ fp_gather_kernel(const __grid_constant__ FastArgs A)
 // ---- plan construction (setup, once per pattern) -----------------------------------------------
 // sort key: window | number of adjacent cells | hash of the local indices; the radix sort is stable, so equal
 // signatures stay in column order
-__global__ void fp_key_kernel(long long ncols, const long long *__restrict__ adjptr, const unsigned char *__restrict__ adjloc,
-                              unsigned long long *__restrict__ key, int *__restrict__ col)
+// (columns = the list `cols` of block-local column ids, ascending; the window is taken over the list index)
+__global__ void fp_key_kernel(long long ncols, const int *__restrict__ cols, const long long *__restrict__ adjptr,
+                              const unsigned char *__restrict__ adjloc, unsigned long long *__restrict__ key, int *__restrict__ col)
 {
     long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= ncols) return;
-    long long p0 = adjptr[k], p1 = adjptr[k + 1];
+    const int kc = cols[k];
+    long long p0 = adjptr[kc], p1 = adjptr[kc + 1];
     unsigned long long h = 1469598103934665603ull;
     for (long long p = p0; p < p1; ++p) { h ^= adjloc[p]; h *= 1099511628211ull; }
     unsigned long long cnt = (unsigned long long)min((long long)255, p1 - p0);
     key[k] = ((unsigned long long)(k / FP_WINDOW) << 42) | (cnt << 34) | ((h ^ (h >> 34)) & ((1ull << 34) - 1));
-    col[k] = (int)k;
+    col[k] = kc;
 }
 
 // one CTA per chunk of FP_T sorted slots: slot -> column, accumulator offsets, chunk total, rounds per warp
@@ -509,7 +533,8 @@ template <typename PosT>
 __global__ void fp_fill_kernel(long long nslots, int ns, int rw, int posstride, const int *__restrict__ slotcol,
                                const int *__restrict__ warpniter, const long long *__restrict__ warpoff,
                                const long long *__restrict__ adjptr, const int *__restrict__ adjcell,
-                               const unsigned char *__restrict__ adjloc, const PosT *__restrict__ posmap, unsigned *__restrict__ rec)
+                               const unsigned char *__restrict__ adjloc, const PosT *__restrict__ posmap, unsigned *__restrict__ rec,
+                               const GeoLayout Lg)
 {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslots) return;
@@ -524,7 +549,7 @@ __global__ void fp_fill_kernel(long long nslots, int ns, int rw, int posstride, 
         unsigned w[4] = {0xffffffffu, 0, 0, 0};
         long long p = p0 + r;
         if (p < p1) {
-            w[0] = (unsigned)adjcell[p] | ((unsigned)adjloc[p] << FP_CELLBITS);
+            w[0] = (unsigned)(Lg.soa ? geo_perm(Lg, adjcell[p]) : (long long)adjcell[p]) | ((unsigned)adjloc[p] << FP_CELLBITS);
             for (int t = 0; t < ns; ++t) w[1 + t / 4] |= ((unsigned)posmap[p * posstride + t] & 0xff) << (8 * (t % 4));
         }
         for (int j = 0; j < rw; ++j) out[(size_t)r * 32 * rw + j] = w[j];

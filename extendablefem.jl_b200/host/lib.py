@@ -22,7 +22,7 @@ EXPORTS = [
     "extfem_space_set", "extfem_space_set_tables", "extfem_pattern_build", "extfem_pattern_dims",
     "extfem_pattern_get", "extfem_assemble_bilinear", "extfem_assemble_linear", "extfem_assemble_nonlinear",
     "extfem_quadrature_points", "extfem_values_get", "extfem_values_set", "extfem_device_ptrs",
-    "extfem_apply_penalties", "extfem_residual", "extfem_spmv", "extfem_cg",
+    "extfem_apply_penalties", "extfem_residual", "extfem_spmv", "extfem_cg", "extfem_plan_stats",
 ]
 
 
@@ -270,6 +270,13 @@ class Engine:
 
     def synchronize(self):
         self._check(self.lib.extfem_synchronize(self.ctx))
+
+    def plan_stats(self, pattern: int, block: int = 0) -> dict:
+        """Statistics of the scatter-map plans of a diagonal block (after its first fast-path assembly)."""
+        st = (C.c_int64 * 8)()
+        self._check(self.lib.extfem_plan_stats(self.ctx, pattern, block, st))
+        keys = ["period", "templates", "template_warps", "record_columns", "template_ctas", "pool_bytes", "template_rounds", "columns"]
+        return dict(zip(keys, [int(v) for v in st]))
 
     def launch_count(self) -> int:
         return int(self.lib.extfem_launch_count(self.ctx))

@@ -121,6 +121,8 @@ int extfem_kernel_id(const char *name);              /* <0: EXTFEM_ERR_UNREGISTE
 int extfem_synchronize(extfem_ctx *ctx);
 /* engine options: "fastpath" (default 1): 0 forces the generic two-phase path for every operator */
 int extfem_set_option(extfem_ctx *ctx, const char *key, int value);
+/* further options: "fastpath_closed_form" (1), "fastpath_templates" (1): 0 keeps every column on the per-pair
+ * record kernel, "template_min_cols" (24): smallest group of structurally identical columns that gets a template */
 /* number of kernel launches issued by this context since creation (bench "gpu_launches") */
 int64_t extfem_launch_count(extfem_ctx *ctx);
 /* device time in ms of the phases of the last assemble call (CUDA events):
@@ -164,6 +166,10 @@ int extfem_assemble_linear(extfem_ctx *ctx, int pattern, const extfem_opdesc *op
                            int accumulate, double *b_out);
 int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, const double *sol,
                               int accumulate, double *nzval_out, double *b_out);
+/* statistics of the scatter-map plans of diagonal block `block` (built on first fast-path use), stats8 =
+ * { period P of the geometry order, templates, template warps, columns on the record kernel, CTAs of the template
+ *   kernel, shared-memory pool bytes, template rounds, columns of the block }                                    */
+int extfem_plan_stats(extfem_ctx *ctx, int pattern, int block, int64_t *stats8);
 /* x at the quadrature points the operator will use: xq[ncells][nq][dim]; *nq_out = nq.
  * xq may be NULL to query nq only.  (Host evaluates its closure there -> EXTFEM_LIN_TABULATED.) */
 int extfem_quadrature_points(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, int is_linear, int *nq_out,

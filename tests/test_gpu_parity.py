@@ -75,6 +75,94 @@ def test_fastpath_equals_generic(pkg, ora, engine, dim, order):
             check_values(b, ref, what="fast (table evaluator) vs oracle")
 
 
+@pytest.mark.parametrize("dim,order,n", [(3, 2, 7), (3, 1, 8), (2, 2, 12), (2, 1, 12)])
+def test_template_path(pkg, ora, engine, dim, order, n):
+    """Template (dictionary-compressed scatter map) kernels: structured grid, templates forced for small groups so that
+    nearly every column runs on the template kernel; first-touch and accumulate modes; against the record kernel
+    (templates off), the generic path and the oracle; the fast RHS on the same plan."""
+    X = np.linspace(0, 1, n + 1)
+    g = pkg.simplexgrid(*([X] * dim))
+    g.cellregions[1::5] = 2
+    engine.set_option("template_min_cols", 2)
+    try:
+        S = System(pkg, ora, engine, g, [pkg.H1Pk(1, dim, order)])
+        for op in (GRAD, ID):
+            for regions in ((), (1,)):
+                desc = engine.make_opdesc([(0, op)], [(0, op)], factor=0.75, regions=regions)
+                a = np.empty(S.rowval.size); b = np.empty(S.rowval.size)
+                engine.assemble_bilinear(S.pat, desc, nzval_out=a)
+                st = engine.plan_stats(S.pat, 0)
+                assert st["templates"] > 0 and st["template_warps"] > 0, st
+                assert st["record_columns"] < st["columns"] // 2, st
+                ref = ora.assemble_bilinear(S.omesh, S.oargs([(0, op)]), S.oargs([(0, op)]), factor=0.75, regions=list(regions),
+                                            csc=(S.colptr, S.rowval))
+                check_values(a, ref, what="template vs oracle")
+                engine.assemble_bilinear(S.pat, desc, accumulate=True, nzval_out=b)
+                check_values(b, 2 * ref, what="template accumulate")
+                engine.set_option("fastpath", 0)
+                try:
+                    engine.assemble_bilinear(S.pat, desc, nzval_out=b)
+                finally:
+                    engine.set_option("fastpath", 1)
+                check_values(a, b, rtol=1e-13, what="template vs generic")
+        # the same system with templates switched off: record kernel only, identical sums
+        engine.set_option("fastpath_templates", 0)
+        try:
+            S2 = System(pkg, ora, engine, g, [pkg.H1Pk(1, dim, order)])
+            desc = engine.make_opdesc([(0, GRAD)], [(0, GRAD)], factor=0.75)
+            c = np.empty(S2.rowval.size)
+            engine.assemble_bilinear(S2.pat, desc, nzval_out=c)
+            assert engine.plan_stats(S2.pat, 0)["templates"] == 0
+        finally:
+            engine.set_option("fastpath_templates", 1)
+        engine.assemble_bilinear(S.pat, desc, nzval_out=a)
+        check_values(a, c, rtol=1e-13, what="template vs record kernel")
+        # fast RHS on the template plan
+        for kernel, params in (("xy", []), ("sincos301", [1.3]), ("constant_one", [])):
+            d = engine.make_opdesc([(0, ID)], kernel_id=pkg.lib.kernel_id(kernel), params=params, factor=2.0, regions=(1,))
+            rb = np.empty(S.N)
+            engine.assemble_linear(S.pat, d, b_out=rb)
+            ref = np.zeros(S.N)
+            ora.assemble_linear(S.omesh, S.oargs([(0, ID)]), ref, kernel, params=params, factor=2.0, regions=[1])
+            check_values(rb, ref, what="template rhs")
+            engine.assemble_linear(S.pat, d, accumulate=True, b_out=rb)
+            check_values(rb, 2 * ref, what="template rhs accumulate")
+            engine.set_option("fastpath", 0)
+            try:
+                rg = np.empty(S.N)
+                engine.assemble_linear(S.pat, d, b_out=rg)
+            finally:
+                engine.set_option("fastpath", 1)
+            check_values(rg, ref, what="generic rhs")
+    finally:
+        engine.set_option("template_min_cols", 24)
+
+
+def test_template_path_block_system(pkg, ora, engine):
+    """Two-block pattern (u, p): the Laplace fast path on block 0 must leave the other blocks' rows zero (no first-touch
+    stores there) and the fast RHS must zero the other row blocks."""
+    X = np.linspace(0, 1, 9)
+    g = pkg.simplexgrid(X, X)
+    engine.set_option("template_min_cols", 2)
+    try:
+        S = System(pkg, ora, engine, g, [pkg.H1Pk(1, 2, 2), pkg.H1Pk(1, 2, 1)])
+        desc = engine.make_opdesc([(0, GRAD)], [(0, GRAD)], factor=1.5)
+        a = np.empty(S.rowval.size)
+        engine.values_set(S.pat, nzval=np.full(S.rowval.size, 7.0), b=np.full(S.N, 7.0))
+        engine.assemble_bilinear(S.pat, desc, nzval_out=a)
+        assert engine.plan_stats(S.pat, 0)["templates"] > 0
+        ref = ora.assemble_bilinear(S.omesh, S.oargs([(0, GRAD)]), S.oargs([(0, GRAD)]), factor=1.5, csc=(S.colptr, S.rowval))
+        check_values(a, ref, what="block system template")
+        d = engine.make_opdesc([(1, ID)], kernel_id=pkg.lib.kernel_id("xy"))
+        rb = np.empty(S.N)
+        engine.assemble_linear(S.pat, d, b_out=rb)
+        rref = np.zeros(S.N)
+        ora.assemble_linear(S.omesh, S.oargs([(1, ID)]), rref, "xy")
+        check_values(rb, rref, what="block system rhs")
+    finally:
+        engine.set_option("template_min_cols", 24)
+
+
 def test_fastpath_large_unstructured_like(pkg, ora, engine):
     """Larger perturbed 3D P2 grid: many chunks of every shared-memory class, ragged warps, boundary columns."""
     X = np.linspace(0, 1, 10)
