@@ -700,12 +700,21 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hidx.data(), widx2.p, (size_t)nwarps * 4, cudaMemcpyDeviceToHost));
     int pool = TP_POOL_BYTES / 8;
     for (int w = 0; w < nwarps; ++w) pool = std::max(pool, (hw[w].y >> 16) * TP_LD);
-    int cur_w = 0, cur_s = 0;
+    // inside windows of the launch order, warps of similar cost (template rounds) go to the same CTA: a CTA's shared
+    // memory and registers are held until its longest warp finishes
+    for (int i0 = 0; i0 < nwarps; i0 += TP_WINDOW) {
+        const int i1 = std::min(nwarps, i0 + TP_WINDOW);
+        std::stable_sort(hidx.begin() + i0, hidx.begin() + i1, [&](int x, int y) { return (hw[x].y & 0xffff) > (hw[y].y & 0xffff); });
+    }
+    int cur_w = 0, cur_s = 0, cur_m = -1;
     ctaw0.push_back(0);
     for (int i = 0; i < nwarps; ++i) {
         const int4 d = hw[hidx[i]];
+        const int mm = d.y & 0xffff;
         const int need = (d.y >> 16) * TP_LD;
-        if (cur_w == TP_MAXW || cur_s + need > pool) { ctaw0.push_back(i); cur_w = 0; cur_s = 0; }
+        // new CTA: full, out of shared memory, or this warp is much cheaper than the CTA's first (longest) one
+        if (cur_w > 0 && (cur_w == TP_MAXW || cur_s + need > pool || 2 * mm < cur_m)) { ctaw0.push_back(i); cur_w = 0; cur_s = 0; }
+        if (cur_w == 0) cur_m = mm;
         launch[i] = make_int4(d.x, d.y, d.z, cur_s);
         cur_s += need; ++cur_w;
     }
@@ -808,14 +817,14 @@ static int build_fast_plan(Ctx *ctx, Pattern &P, int b, int ns)
     return 0;
 }
 
-template <class EV, bool FIRST>
+template <class EV>
 static int launch_template(Ctx *ctx, Pattern &P, TemplatePlan &T, int b, int accumulate)
 {
     TPArgs A;
     A.ctaw0 = T.ctaw0.as<int>(); A.wdesc = T.wdesc.as<int4>(); A.slotcol = T.slotcol.as<int>(); A.slotpb = T.slotpb.as<int>();
     A.tmpl = T.tmpl.as<unsigned>(); A.colptr = P.colptr.as<long long>() + P.coloff[b]; A.nzval = P.nzval.as<double>();
     A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
-    auto k = tp_gather_kernel<EV, FIRST>;
+    auto k = tp_gather_kernel<EV>;
     static bool attr_set = false;
     if (!attr_set) {
         EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -842,10 +851,7 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
     LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (SOA && T.nwarps > 0) {
-        // first-touch stores need: overwrite, and column segments that hold rows of this block only
-        const bool first = !accumulate && P.rowspaces.size() == 1;
-        if (int rc = first ? launch_template<EV, true>(ctx, P, T, b, accumulate) : launch_template<EV, false>(ctx, P, T, b, accumulate))
-            return rc;
+        if (int rc = launch_template<EV>(ctx, P, T, b, accumulate)) return rc;
     }
     if (F.nchunks > 0) {
         FastArgs A;
