@@ -54,7 +54,7 @@ struct TemplatePlan {
     GeoLayout Lg{0, 1, 0, 0};
     int nwarps = 0, nctas = 0, ngroups = 0, ntemplates = 0, pool_bytes = 0;
     long long nrounds = 0, nleft = 0, ncols = 0;
-    DevBuf ctaw0, wdesc, slotcol, slotpb, tmpl, leftcols;
+    DevBuf wdesc, slotcol, slotpb, slotptr, tmpl, leftcols, dump;
 };
 
 struct Pattern {
@@ -645,10 +645,10 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     if (nwarps == 0 || nrounds >= (1ll << 31) - 1) return all_left();
 
     // slots, warp descriptors (template order), leftover columns
-    DevBuf wd0, wkey, wkey2, widx, widx2, left, leftsel, nsel;
+    DevBuf wd0, wkey, wkey2, widx, widx2, left, leftsel, nsel, slotcol0, slotpb0;
     if (int rc = ensure(ctx, T.tmpl, (size_t)nrounds * TP_TW * 4)) return rc;
-    if (int rc = ensure(ctx, T.slotcol, (size_t)nwarps * 32 * 4)) return rc;
-    if (int rc = ensure(ctx, T.slotpb, (size_t)nwarps * 32 * 4)) return rc;
+    if (int rc = ensure(ctx, slotcol0, (size_t)nwarps * 32 * 4)) return rc;
+    if (int rc = ensure(ctx, slotpb0, (size_t)nwarps * 32 * 4)) return rc;
     if (int rc = ensure(ctx, wd0, (size_t)nwarps * 16)) return rc;
     if (int rc = ensure(ctx, wkey, (size_t)nwarps * 4)) return rc;
     if (int rc = ensure(ctx, wkey2, (size_t)nwarps * 4)) return rc;
@@ -657,14 +657,14 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     if (int rc = ensure(ctx, left, ncols)) return rc;
     if (int rc = ensure(ctx, leftsel, ncols * 4)) return rc;
     if (int rc = ensure(ctx, nsel, 8)) return rc;
-    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(T.slotcol.p, 0xff, (size_t)nwarps * 32 * 4, st));
-    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(T.slotpb.p, 0, (size_t)nwarps * 32 * 4, st));
+    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(slotcol0.p, 0xff, (size_t)nwarps * 32 * 4, st));
+    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(slotpb0.p, 0, (size_t)nwarps * 32 * 4, st));
     tp_tmpl_kernel<<<nblocks(ngroups, 128), 128, 0, st>>>(ngroups, ns, posstride, Lg, gstart.as<int>(), order.as<int>(), gnr.as<long long>(),
                                                           gr0.as<long long>(), adjptr, adjcell, adjloc, posmap, T.tmpl.as<unsigned>());
     LAUNCHED(ctx);
     tp_slot_kernel<<<gb, 256, 0, st>>>(ncols, Lg, order.as<int>(), gid1.as<int>(), gstart.as<int>(), gnw.as<int>(), gw0.as<int>(),
                                        gnr.as<long long>(), gr0.as<long long>(), ok.as<unsigned char>(), base.as<int>(), colptr,
-                                       T.slotcol.as<int>(), T.slotpb.as<int>(), wd0.as<int4>(), wkey.as<unsigned>(), widx.as<int>(),
+                                       slotcol0.as<int>(), slotpb0.as<int>(), wd0.as<int4>(), wkey.as<unsigned>(), widx.as<int>(),
                                        left.as<unsigned char>());
     LAUNCHED(ctx);
     {
@@ -694,32 +694,55 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     // launch order: warps sorted by the first adjacent cell of their first column, so that all templates sweep the
     // mesh together (geometry is read from DRAM once, output streams advance sequentially)
     if (int rc = radix_sort_pairs(ctx, wkey.as<unsigned>(), wkey2.as<unsigned>(), widx.as<int>(), widx2.as<int>(), nwarps)) return rc;
-    std::vector<int4> hw((size_t)nwarps), launch((size_t)nwarps);
-    std::vector<int> hidx((size_t)nwarps), ctaw0;
+    std::vector<int4> hw((size_t)nwarps);
+    std::vector<int> hidx((size_t)nwarps);
     EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hw.data(), wd0.p, (size_t)nwarps * 16, cudaMemcpyDeviceToHost));
     EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hidx.data(), widx2.p, (size_t)nwarps * 4, cudaMemcpyDeviceToHost));
+    auto wneed = [&](const int4 &d) { return (tp_warp_smem(d.y >> 16, d.y & 0xffff) + 1) & ~1; }; // doubles, even
     int pool = TP_POOL_BYTES / 8;
-    for (int w = 0; w < nwarps; ++w) pool = std::max(pool, (hw[w].y >> 16) * TP_LD);
+    for (int w = 0; w < nwarps; ++w) pool = std::max(pool, wneed(hw[w]));
     // inside windows of the launch order, warps of similar cost (template rounds) go to the same CTA: a CTA's shared
     // memory and registers are held until its longest warp finishes
     for (int i0 = 0; i0 < nwarps; i0 += TP_WINDOW) {
         const int i1 = std::min(nwarps, i0 + TP_WINDOW);
         std::stable_sort(hidx.begin() + i0, hidx.begin() + i1, [&](int x, int y) { return (hw[x].y & 0xffff) > (hw[y].y & 0xffff); });
     }
+    // CTAs are padded to TP_MAXW descriptors (rounds == 0: the warp exits), so that warp q = blockIdx * TP_MAXW + warp
+    std::vector<int4> launch;
+    std::vector<int> wpos((size_t)nwarps);
+    launch.reserve((size_t)nwarps + nwarps / 2);
     int cur_w = 0, cur_s = 0, cur_m = -1;
-    ctaw0.push_back(0);
+    auto close_cta = [&]() { while (launch.size() % TP_MAXW) launch.push_back(make_int4(0, 0, 0, 0)); cur_w = 0; cur_s = 0; };
     for (int i = 0; i < nwarps; ++i) {
         const int4 d = hw[hidx[i]];
         const int mm = d.y & 0xffff;
-        const int need = (d.y >> 16) * TP_LD;
+        const int need = wneed(d);
         // new CTA: full, out of shared memory, or this warp is much cheaper than the CTA's first (longest) one
-        if (cur_w > 0 && (cur_w == TP_MAXW || cur_s + need > pool || 2 * mm < cur_m)) { ctaw0.push_back(i); cur_w = 0; cur_s = 0; }
+        if (cur_w > 0 && (cur_w == TP_MAXW || cur_s + need > pool || 2 * mm < cur_m)) close_cta();
         if (cur_w == 0) cur_m = mm;
-        launch[i] = make_int4(d.x, d.y, d.z, cur_s);
+        wpos[hidx[i]] = (int)launch.size();
+        launch.push_back(make_int4(d.x, d.y, cur_s, 0));
         cur_s += need; ++cur_w;
     }
-    ctaw0.push_back(nwarps);
-    T.nctas = (int)ctaw0.size() - 1;
+    close_cta();
+    T.nctas = (int)(launch.size() / TP_MAXW);
+    const long long nslots_l = (long long)launch.size() * 32;
+    if (int rc = ensure(ctx, T.slotcol, (size_t)nslots_l * 4)) return rc;
+    if (int rc = ensure(ctx, T.slotpb, (size_t)nslots_l * 4)) return rc;
+    if (int rc = ensure(ctx, T.slotptr, (size_t)nslots_l * 8)) return rc;
+    if (int rc = ensure(ctx, T.dump, 512 * 8)) return rc;
+    {
+        DevBuf dwpos;
+        if (int rc = upload(ctx, dwpos, wpos.data(), wpos.size() * 4)) return rc;
+        tp_slot_init_kernel<<<nblocks(nslots_l, 256), 256, 0, st>>>(nslots_l, T.dump.as<double>(), T.slotcol.as<int>(), T.slotpb.as<int>(),
+                                                                  T.slotptr.as<double *>());
+        LAUNCHED(ctx);
+        tp_slot_permute_kernel<<<nblocks((long long)nwarps * 32, 256), 256, 0, st>>>(
+            (long long)nwarps * 32, dwpos.as<int>(), slotcol0.as<int>(), slotpb0.as<int>(), colptr, P.nzval.as<double>(),
+            T.dump.as<double>(), T.slotcol.as<int>(), T.slotpb.as<int>(), T.slotptr.as<double *>());
+        LAUNCHED(ctx);
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    }
     T.nwarps = nwarps;
     T.nrounds = nrounds;
     T.pool_bytes = pool * 8;
@@ -731,7 +754,6 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
         for (int g = 0; g < ngroups; ++g) T.ntemplates += hnw[g] > 0;
     }
     if (int rc = upload(ctx, T.wdesc, launch.data(), launch.size() * 16)) return rc;
-    if (int rc = upload(ctx, T.ctaw0, ctaw0.data(), ctaw0.size() * 4)) return rc;
     EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
     EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
     return 0;
@@ -821,9 +843,9 @@ template <class EV>
 static int launch_template(Ctx *ctx, Pattern &P, TemplatePlan &T, int b, int accumulate)
 {
     TPArgs A;
-    A.ctaw0 = T.ctaw0.as<int>(); A.wdesc = T.wdesc.as<int4>(); A.slotcol = T.slotcol.as<int>(); A.slotpb = T.slotpb.as<int>();
-    A.tmpl = T.tmpl.as<unsigned>(); A.colptr = P.colptr.as<long long>() + P.coloff[b]; A.nzval = P.nzval.as<double>();
-    A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
+    A.wdesc = T.wdesc.as<int4>(); A.slotpb = T.slotpb.as<int>(); A.slotptr = T.slotptr.as<double *>();
+    A.tmpl = T.tmpl.as<unsigned>(); A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
+    (void)P; (void)b;
     auto k = tp_gather_kernel<EV>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1081,9 +1103,9 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (T.nwarps > 0) {
         TPRhsArgs A;
-        A.nwarps = T.nwarps; A.wdesc = T.wdesc.as<int4>(); A.slotcol = T.slotcol.as<int>(); A.slotpb = T.slotpb.as<int>();
+        A.nwarps = T.nctas * TP_MAXW; A.wdesc = T.wdesc.as<int4>(); A.slotcol = T.slotcol.as<int>(); A.slotpb = T.slotpb.as<int>();
         A.tmpl = T.tmpl.as<unsigned>(); A.fq = ctx->fq.as<double>(); A.Npad = T.Lg.Npad; A.nq = op.nq; A.b = bblk; A.overwrite = !accumulate;
-        tp_rhs_kernel<<<nblocks(T.nwarps, 8), 256, 0, ctx->stream>>>(A);
+        tp_rhs_kernel<<<nblocks((long long)T.nctas * TP_MAXW, 8), 256, 0, ctx->stream>>>(A);
         LAUNCHED(ctx);
     }
     if (T.nleft > 0) {
