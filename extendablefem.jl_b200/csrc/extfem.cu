@@ -839,14 +839,14 @@ static int build_fast_plan(Ctx *ctx, Pattern &P, int b, int ns)
     return 0;
 }
 
-template <class EV>
+template <class EV, bool FIRST>
 static int launch_template(Ctx *ctx, Pattern &P, TemplatePlan &T, int b, int accumulate)
 {
     TPArgs A;
     A.wdesc = T.wdesc.as<int4>(); A.slotpb = T.slotpb.as<int>(); A.slotptr = T.slotptr.as<double *>();
     A.tmpl = T.tmpl.as<unsigned>(); A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
     (void)P; (void)b;
-    auto k = tp_gather_kernel<EV>;
+    auto k = tp_gather_kernel<EV, FIRST>;
     static bool attr_set = false;
     if (!attr_set) {
         EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -873,7 +873,10 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
     LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (SOA && T.nwarps > 0) {
-        if (int rc = launch_template<EV>(ctx, P, T, b, accumulate)) return rc;
+        // first-touch stores need: overwrite, and column segments that hold rows of this block only
+        const bool first = !accumulate && P.rowspaces.size() == 1;
+        if (int rc = first ? launch_template<EV, true>(ctx, P, T, b, accumulate) : launch_template<EV, false>(ctx, P, T, b, accumulate))
+            return rc;
     }
     if (F.nchunks > 0) {
         FastArgs A;
@@ -1105,7 +1108,12 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
         TPRhsArgs A;
         A.nwarps = T.nctas * TP_MAXW; A.wdesc = T.wdesc.as<int4>(); A.slotcol = T.slotcol.as<int>(); A.slotpb = T.slotpb.as<int>();
         A.tmpl = T.tmpl.as<unsigned>(); A.fq = ctx->fq.as<double>(); A.Npad = T.Lg.Npad; A.nq = op.nq; A.b = bblk; A.overwrite = !accumulate;
-        tp_rhs_kernel<<<nblocks((long long)T.nctas * TP_MAXW, 8), 256, 0, ctx->stream>>>(A);
+        const unsigned gr = nblocks((long long)T.nctas * TP_MAXW, 8);
+        if (op.nq == 1) tp_rhs_kernel<1><<<gr, 256, 0, ctx->stream>>>(A);
+        else if (op.nq == 3) tp_rhs_kernel<3><<<gr, 256, 0, ctx->stream>>>(A);
+        else if (op.nq == 4) tp_rhs_kernel<4><<<gr, 256, 0, ctx->stream>>>(A);
+        else if (op.nq == 6) tp_rhs_kernel<6><<<gr, 256, 0, ctx->stream>>>(A);
+        else tp_rhs_kernel<0><<<gr, 256, 0, ctx->stream>>>(A);
         LAUNCHED(ctx);
     }
     if (T.nleft > 0) {
