@@ -98,6 +98,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     eng = pkg.lib.Engine(local_rank)
+    for kv in filter(None, os.environ.get("EXTFEM_OPTIONS", "").split(",")):   # tuning knobs, e.g. template_pool_bytes=57344
+        k, v = kv.split("=")
+        eng.set_option(k.strip(), int(v))
     t0 = time.time()
     grid, FES = build_problem(pkg, args.n, rank, world)
     t_mesh = time.time() - t0

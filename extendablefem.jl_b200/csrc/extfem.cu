@@ -104,6 +104,8 @@ struct Ctx {
     DevBuf loc, bloc, sol, params_scratch, tab, geo, visit, fq;
     bool fast_enabled = true;   // option "fastpath"
     bool tmpl_enabled = true;   // option "fastpath_templates": 0 keeps every column on the record kernel
+    int tmpl_ahead = 1024;      // option "template_prefetch_ctas": CTAs ahead whose start-up data is prefetched into L2
+    int tmpl_pool = TP_POOL_BYTES; // option "template_pool_bytes": shared-memory pool of one template CTA
     int tmpl_mincols = 24;      // option "template_min_cols": smallest group of columns that gets a template
     bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator
     long long launches = 0;
@@ -699,7 +701,7 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hw.data(), wd0.p, (size_t)nwarps * 16, cudaMemcpyDeviceToHost));
     EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hidx.data(), widx2.p, (size_t)nwarps * 4, cudaMemcpyDeviceToHost));
     auto wneed = [&](const int4 &d) { return (tp_warp_smem(d.y >> 16, d.y & 0xffff) + 1) & ~1; }; // doubles, even
-    int pool = TP_POOL_BYTES / 8;
+    int pool = ctx->tmpl_pool / 8;
     for (int w = 0; w < nwarps; ++w) pool = std::max(pool, wneed(hw[w]));
     // inside windows of the launch order, warps of similar cost (template rounds) go to the same CTA: a CTA's shared
     // memory and registers are held until its longest warp finishes
@@ -845,6 +847,7 @@ static int launch_template(Ctx *ctx, Pattern &P, TemplatePlan &T, int b, int acc
     TPArgs A;
     A.wdesc = T.wdesc.as<int4>(); A.slotpb = T.slotpb.as<int>(); A.slotptr = T.slotptr.as<double *>();
     A.tmpl = T.tmpl.as<unsigned>(); A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
+    A.nwarps = T.nctas * TP_MAXW; A.ahead = ctx->tmpl_ahead * TP_MAXW;
     (void)P; (void)b;
     auto k = tp_gather_kernel<EV, FIRST>;
     static bool attr_set = false;
@@ -1216,6 +1219,8 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "fastpath")) { C->fast_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_closed_form")) { C->bary_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_prefetch_ctas")) { C->tmpl_ahead = value < 0 ? 0 : value; return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_pool_bytes")) { C->tmpl_pool = std::min(std::max(value, 4096), 200 * 1024); return EXTFEM_OK; }
     if (key && !strcmp(key, "template_min_cols")) { C->tmpl_mincols = value < 1 ? 1 : value; return EXTFEM_OK; }
     return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("unknown option ") + (key ? key : "(null)"));
 }
