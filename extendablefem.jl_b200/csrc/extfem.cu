@@ -14,6 +14,7 @@
 #include "fastpath.cuh"
 #include "fastplan.cuh"
 #include "solver.cuh"
+#include "dist.cuh"
 
 namespace extfem {
 
@@ -75,6 +76,7 @@ struct Pattern {
     int nchunks = 0;
     bool square = false;
     SolverWork cg;
+    IfacePlan iface;                           // partition interfaces (multi-GPU)
 };
 
 struct TableKey {
@@ -94,6 +96,7 @@ struct DevQuad {
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    DistState dist;
     std::string err;
     std::vector<std::unique_ptr<Mesh>> meshes;
     std::vector<std::unique_ptr<Space>> spaces;
@@ -1179,6 +1182,7 @@ int extfem_ctx_destroy(extfem_ctx *ctx)
     for (auto &ev : C->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : C->uev) if (ev) cudaEventDestroy(ev);
     C->patterns.clear(); C->spaces.clear(); C->meshes.clear();
+    if (C->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(C->dist.comm);
     cudaStream_t s = C->stream;
     delete C;
     cudaStreamDestroy(s);
@@ -1728,4 +1732,129 @@ int extfem_cg(extfem_ctx *ctx, int pattern, const double *b, double *x, double r
     return EXTFEM_OK;
 }
 
+/* ---- multi-GPU: one process per GPU, NCCL communicator inside the context (dist.cuh) ---------------------- */
+int extfem_dist_unique_id(char *id128)
+{
+    if (!id128) return fail(nullptr, EXTFEM_ERR_BAD_ARGUMENT, "id128 is NULL");
+    std::string e = g_nccl.load();
+    if (!e.empty()) return fail(nullptr, EXTFEM_ERR_NCCL, e);
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, EXTFEM_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+    memcpy(id128, &id, 128);
+    return EXTFEM_OK;
+}
+
+int extfem_dist_init(extfem_ctx *ctx, int rank, int world, const char *id128)
+{
+    CTX_GUARD(ctx);
+    if (world < 1 || rank < 0 || rank >= world) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_init: bad rank / world");
+    C->dist.rank = rank; C->dist.world = world;
+    if (world > 1) {
+        if (!id128) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_init: id128 is NULL");
+        std::string e = g_nccl.load();
+        if (!e.empty()) return fail(C, EXTFEM_ERR_NCCL, e);
+        ncclUniqueId id;
+        memcpy(&id, id128, 128);
+        ncclResult_t r = g_nccl.CommInitRank(&C->dist.comm, world, id, rank);
+        if (r != ncclSuccess) return fail(C, EXTFEM_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+    }
+    C->dist.ready = true;
+    return EXTFEM_OK;
+}
+
+int extfem_dist_set_interfaces(extfem_ctx *ctx, int pattern, int nneigh, const int32_t *neigh_ranks, const int64_t *ptr,
+                               const int64_t *rows, const uint8_t *owned)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (!C->dist.ready) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_init has not been called");
+    if (nneigh < 0 || (nneigh > 0 && (!neigh_ranks || !ptr || !rows))) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_set_interfaces: bad argument");
+    IfacePlan &I = P.iface;
+    I.ranks.assign(neigh_ranks, neigh_ranks + nneigh);
+    I.ptr.assign(1, 0);
+    for (int k = 0; k < nneigh; ++k) {
+        if (ptr[k + 1] < ptr[k] || neigh_ranks[k] < 0 || neigh_ranks[k] >= C->dist.world || neigh_ranks[k] == C->dist.rank)
+            return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_set_interfaces: bad neighbour list");
+        I.ptr.push_back(ptr[k + 1] - ptr[0]);
+    }
+    const long long ntot = I.ptr.back();
+    std::vector<int> r0((size_t)std::max(ntot, 1ll));
+    for (long long i = 0; i < ntot; ++i) {
+        long long r = rows[ptr[0] + i] - 1;
+        if (r < 0 || r >= P.nrows) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_set_interfaces: row out of range");
+        r0[i] = (int)r;
+    }
+    std::vector<double> w((size_t)P.nrows, 1.0);
+    if (owned) for (long long i = 0; i < P.nrows; ++i) w[i] = owned[i] ? 1.0 : 0.0;
+    for (void **p : {&I.rows, &I.sendbuf, &I.recvbuf, &I.weight}) if (*p) { cudaFree(*p); *p = nullptr; }
+    EXTFEM_CUDA_CHECK(C, cudaMalloc(&I.rows, r0.size() * 4));
+    EXTFEM_CUDA_CHECK(C, cudaMalloc(&I.sendbuf, r0.size() * 8));
+    EXTFEM_CUDA_CHECK(C, cudaMalloc(&I.recvbuf, r0.size() * 8));
+    EXTFEM_CUDA_CHECK(C, cudaMalloc(&I.weight, w.size() * 8));
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(I.rows, r0.data(), r0.size() * 4, cudaMemcpyHostToDevice, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(I.weight, w.data(), w.size() * 8, cudaMemcpyHostToDevice, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    I.ready = true;
+    return EXTFEM_OK;
+}
+
+#define GET_IFACE()                                                                                    \
+    if (!C->dist.ready || !P.iface.ready)                                                              \
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_init / extfem_dist_set_interfaces have not been called");
+
+int extfem_dist_sum_rhs(extfem_ctx *ctx, int pattern)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    GET_IFACE();
+    std::string e;
+    if (iface_exchange_add(C->stream, C->dist, P.iface, P.b.as<double>(), &C->launches, &e)) return fail(C, EXTFEM_ERR_NCCL, e.empty() ? "interface exchange failed" : e);
+    return EXTFEM_OK;
+}
+
+int extfem_dist_spmv(extfem_ctx *ctx, int pattern, const double *x, double *y)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    GET_IFACE();
+    if (!x || !y) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "x or y is NULL");
+    DevBuf dx, dy;
+    if (int rc = upload(C, dx, x, (size_t)P.ncols * 8)) return rc;
+    if (int rc = ensure(C, dy, (size_t)P.nrows * 8)) return rc;
+    if (int rc = csc_spmv(C->stream, P.nrows, P.ncols, P.nnz, P.colptr.as<long long>(), P.rowval.as<int>(), P.nzval.as<double>(),
+                          dx.as<double>(), dy.as<double>(), P.cg, &C->launches))
+        return fail(C, EXTFEM_ERR_CUDA, "spmv failed");
+    std::string e;
+    if (iface_exchange_add(C->stream, C->dist, P.iface, dy.as<double>(), &C->launches, &e)) return fail(C, EXTFEM_ERR_NCCL, e.empty() ? "interface exchange failed" : e);
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(y, dy.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    return EXTFEM_OK;
+}
+
+int extfem_dist_cg(extfem_ctx *ctx, int pattern, const double *b, double *x, double rtol, int maxit, int *iters, double *relres)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    GET_IFACE();
+    if (!P.square || P.nrows != P.ncols) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "CG needs a square system");
+    if (!x) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "x is NULL");
+    DevBuf db, dx;
+    const double *bptr = P.b.as<double>();
+    if (b) { if (int rc = upload(C, db, b, (size_t)P.nrows * 8)) return rc; bptr = db.as<double>(); }
+    if (int rc = upload(C, dx, x, (size_t)P.nrows * 8)) return rc;
+    int it = 0; double rr = 0;
+    std::string e;
+    if (int rc = dist_jacobi_cg(C->stream, C->dist, P.iface, P.nrows, P.colptr.as<long long>(), P.rowval.as<int>(), P.nzval.as<double>(), bptr,
+                                dx.as<double>(), rtol, maxit, &it, &rr, P.cg, &C->launches, &e))
+        return fail(C, rc == -5 ? EXTFEM_ERR_NCCL : EXTFEM_ERR_CUDA, "distributed CG failed, code " + std::to_string(rc) + " " + e);
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(x, dx.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    if (iters) *iters = it;
+    if (relres) *relres = rr;
+    return EXTFEM_OK;
+}
+
 } // extern "C"
+

@@ -23,6 +23,7 @@ EXPORTS = [
     "extfem_pattern_get", "extfem_assemble_bilinear", "extfem_assemble_linear", "extfem_assemble_nonlinear",
     "extfem_quadrature_points", "extfem_values_get", "extfem_values_set", "extfem_device_ptrs",
     "extfem_apply_penalties", "extfem_residual", "extfem_spmv", "extfem_cg", "extfem_plan_stats",
+    "extfem_dist_unique_id", "extfem_dist_init", "extfem_dist_set_interfaces", "extfem_dist_sum_rhs", "extfem_dist_spmv", "extfem_dist_cg",
 ]
 
 
@@ -215,10 +216,11 @@ class Engine:
         return xq
 
     # ---- device-resident system ----------------------------------------------------------------
-    def values_get(self, pattern, want_nzval=True, want_b=True):
+    def values_get(self, pattern, want_nzval=True, want_b=True, nzval_out=None, b_out=None):
+        """Device-resident values; ``*_out`` (numpy array / pinned torch tensor / device pointer) receive them in place."""
         nrows, ncols, nnz = self.pattern_dims(pattern)
-        nz = np.empty(nnz) if want_nzval else None
-        b = np.empty(nrows) if want_b else None
+        nz = nzval_out if nzval_out is not None else (np.empty(nnz) if want_nzval else None)
+        b = b_out if b_out is not None else (np.empty(nrows) if want_b else None)
         self._check(self.lib.extfem_values_get(self.ctx, pattern, _p(nz), _p(b)))
         return nz, b
 
@@ -277,6 +279,44 @@ class Engine:
         self._check(self.lib.extfem_plan_stats(self.ctx, pattern, block, st))
         keys = ["period", "templates", "template_warps", "record_columns", "template_ctas", "pool_bytes", "template_rounds", "columns"]
         return dict(zip(keys, [int(v) for v in st]))
+
+    # ---- multi-GPU (one process per GPU) ------------------------------------------------------------
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        lib = load_library()
+        rc = lib.extfem_dist_unique_id(buf)
+        if rc != 0:
+            raise ExtFEMError(rc, lib.extfem_last_error(None).decode())
+        return buf.raw
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes | None = None):
+        self._check(self.lib.extfem_dist_init(self.ctx, int(rank), int(world), unique_id))
+
+    def dist_set_interfaces(self, pattern: int, plan):
+        neigh = np.ascontiguousarray(plan.neigh, dtype=np.int32)
+        ptr = np.ascontiguousarray(plan.ptr, dtype=np.int64)
+        rows = np.ascontiguousarray(plan.rows, dtype=np.int64)
+        owned = np.ascontiguousarray(plan.owned, dtype=np.uint8)
+        self._check(self.lib.extfem_dist_set_interfaces(self.ctx, pattern, int(neigh.size), _p(neigh), _p(ptr), _p(rows), _p(owned)))
+
+    def dist_sum_rhs(self, pattern: int):
+        self._check(self.lib.extfem_dist_sum_rhs(self.ctx, pattern))
+
+    def dist_spmv(self, pattern, x):
+        nrows, _, _ = self.pattern_dims(pattern)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(nrows)
+        self._check(self.lib.extfem_dist_spmv(self.ctx, pattern, _p(x), _p(y)))
+        return y
+
+    def dist_cg(self, pattern, b=None, x0=None, rtol=1e-10, maxit=10000):
+        nrows, _, _ = self.pattern_dims(pattern)
+        x = np.zeros(nrows) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        it, rr = C.c_int(), C.c_double()
+        self._check(self.lib.extfem_dist_cg(self.ctx, pattern, _p(bb), _p(x), C.c_double(rtol), int(maxit), C.byref(it), C.byref(rr)))
+        return x, it.value, rr.value
 
     def launch_count(self) -> int:
         return int(self.lib.extfem_launch_count(self.ctx))

@@ -192,6 +192,26 @@ int extfem_spmv(extfem_ctx *ctx, int pattern, const double *x, double *y);
 int extfem_cg(extfem_ctx *ctx, int pattern, const double *b, double *x, double rtol, int maxit, int *iters,
               double *relres);
 
+/* ---- multi-GPU: one process per GPU, cells partitioned into contiguous ranges.  Every rank assembles
+ *      its own cells into a local system over its local dofs with the calls above; the global system is the SUM of the
+ *      local ones (the reference's analogue: thread-private partitions merged by flush!, bilinear_operator.jl:969-993).
+ *      Only interface-row contributions cross NVLink (grouped ncclSend/ncclRecv between neighbouring ranks on the
+ *      context's stream).  With world == 1 every call below degenerates to its single-GPU meaning.                   */
+int extfem_dist_unique_id(char *id128);                 /* rank 0: ncclGetUniqueId; broadcast the 128 bytes to all ranks */
+int extfem_dist_init(extfem_ctx *ctx, int rank, int world, const char *id128);
+/* rows of `pattern` shared with each neighbouring rank: rows[ptr[k] .. ptr[k+1]) (1-based, local) are shared with
+ * neigh_ranks[k], listed in an order both sides agree on (ascending global dof id); owned[nrows] != 0 marks the rows
+ * this rank owns (every global row is owned by exactly one rank; NULL: all).                                       */
+int extfem_dist_set_interfaces(extfem_ctx *ctx, int pattern, int nneigh, const int32_t *neigh_ranks, const int64_t *ptr,
+                               const int64_t *rows, const uint8_t *owned);
+/* device-resident rhs: b_i <- sum over the ranks sharing row i of their b_i (afterwards b is consistent) */
+int extfem_dist_sum_rhs(extfem_ctx *ctx, int pattern);
+/* y = A x for the sharded matrix: local SpMV + interface sum; x and y are consistent local vectors */
+int extfem_dist_spmv(extfem_ctx *ctx, int pattern, const double *x, double *y);
+/* Jacobi-preconditioned CG on the sharded system; b == NULL uses the (consistent) device-resident rhs */
+int extfem_dist_cg(extfem_ctx *ctx, int pattern, const double *b, double *x, double rtol, int maxit, int *iters,
+                   double *relres);
+
 #ifdef __cplusplus
 }
 #endif
