@@ -652,8 +652,9 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     // slots, warp descriptors (template order), leftover columns
     DevBuf wd0, wkey, wkey2, widx, widx2, left, leftsel, nsel, slotcol0, slotpb0;
     if (int rc = ensure(ctx, T.tmpl, (size_t)nrounds * TP_TW * 4)) return rc;
-    if (int rc = ensure(ctx, slotcol0, (size_t)nwarps * 32 * 4)) return rc;
-    if (int rc = ensure(ctx, slotpb0, (size_t)nwarps * 32 * 4)) return rc;
+    const size_t nslots0 = (size_t)nwarps * 32 * TP_K;   // template order
+    if (int rc = ensure(ctx, slotcol0, nslots0 * 4)) return rc;
+    if (int rc = ensure(ctx, slotpb0, nslots0 * 4)) return rc;
     if (int rc = ensure(ctx, wd0, (size_t)nwarps * 16)) return rc;
     if (int rc = ensure(ctx, wkey, (size_t)nwarps * 4)) return rc;
     if (int rc = ensure(ctx, wkey2, (size_t)nwarps * 4)) return rc;
@@ -662,8 +663,8 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     if (int rc = ensure(ctx, left, ncols)) return rc;
     if (int rc = ensure(ctx, leftsel, ncols * 4)) return rc;
     if (int rc = ensure(ctx, nsel, 8)) return rc;
-    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(slotcol0.p, 0xff, (size_t)nwarps * 32 * 4, st));
-    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(slotpb0.p, 0, (size_t)nwarps * 32 * 4, st));
+    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(slotcol0.p, 0xff, nslots0 * 4, st));
+    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(slotpb0.p, 0, nslots0 * 4, st));
     tp_tmpl_kernel<<<nblocks(ngroups, 128), 128, 0, st>>>(ngroups, ns, posstride, Lg, gstart.as<int>(), order.as<int>(), gnr.as<long long>(),
                                                           gr0.as<long long>(), adjptr, adjcell, adjloc, posmap, T.tmpl.as<unsigned>());
     LAUNCHED(ctx);
@@ -703,14 +704,15 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     std::vector<int> hidx((size_t)nwarps);
     EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hw.data(), wd0.p, (size_t)nwarps * 16, cudaMemcpyDeviceToHost));
     EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hidx.data(), widx2.p, (size_t)nwarps * 4, cudaMemcpyDeviceToHost));
-    auto wneed = [&](const int4 &d) { return (tp_warp_smem(d.y >> 16, d.y & 0xffff) + 1) & ~1; }; // doubles, even
+    auto wneed = [&](const int4 &d) { return (tp_warp_smem(tp_desc_L(d.y), tp_desc_m(d.y)) + 1) & ~1; }; // doubles, even
+    auto wcost = [&](const int4 &d) { return tp_desc_m(d.y) * tp_desc_ng(d.y); };                      // rounds of the warp
     int pool = ctx->tmpl_pool / 8;
     for (int w = 0; w < nwarps; ++w) pool = std::max(pool, wneed(hw[w]));
     // inside windows of the launch order, warps of similar cost (template rounds) go to the same CTA: a CTA's shared
     // memory and registers are held until its longest warp finishes
     for (int i0 = 0; i0 < nwarps; i0 += TP_WINDOW) {
         const int i1 = std::min(nwarps, i0 + TP_WINDOW);
-        std::stable_sort(hidx.begin() + i0, hidx.begin() + i1, [&](int x, int y) { return (hw[x].y & 0xffff) > (hw[y].y & 0xffff); });
+        std::stable_sort(hidx.begin() + i0, hidx.begin() + i1, [&](int x, int y) { return wcost(hw[x]) > wcost(hw[y]); });
     }
     // CTAs are padded to TP_MAXW descriptors (rounds == 0: the warp exits), so that warp q = blockIdx * TP_MAXW + warp
     std::vector<int4> launch;
@@ -720,7 +722,7 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     auto close_cta = [&]() { while (launch.size() % TP_MAXW) launch.push_back(make_int4(0, 0, 0, 0)); cur_w = 0; cur_s = 0; };
     for (int i = 0; i < nwarps; ++i) {
         const int4 d = hw[hidx[i]];
-        const int mm = d.y & 0xffff;
+        const int mm = wcost(d);
         const int need = wneed(d);
         // new CTA: full, out of shared memory, or this warp is much cheaper than the CTA's first (longest) one
         if (cur_w > 0 && (cur_w == TP_MAXW || cur_s + need > pool || 2 * mm < cur_m)) close_cta();
@@ -731,7 +733,7 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     }
     close_cta();
     T.nctas = (int)(launch.size() / TP_MAXW);
-    const long long nslots_l = (long long)launch.size() * 32;
+    const long long nslots_l = (long long)launch.size() * 32 * TP_K;
     if (int rc = ensure(ctx, T.slotcol, (size_t)nslots_l * 4)) return rc;
     if (int rc = ensure(ctx, T.slotpb, (size_t)nslots_l * 4)) return rc;
     if (int rc = ensure(ctx, T.slotptr, (size_t)nslots_l * 8)) return rc;
@@ -742,8 +744,8 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
         tp_slot_init_kernel<<<nblocks(nslots_l, 256), 256, 0, st>>>(nslots_l, T.dump.as<double>(), T.slotcol.as<int>(), T.slotpb.as<int>(),
                                                                   T.slotptr.as<double *>());
         LAUNCHED(ctx);
-        tp_slot_permute_kernel<<<nblocks((long long)nwarps * 32, 256), 256, 0, st>>>(
-            (long long)nwarps * 32, dwpos.as<int>(), slotcol0.as<int>(), slotpb0.as<int>(), colptr, P.nzval.as<double>(),
+        tp_slot_permute_kernel<<<nblocks((long long)nslots0, 256), 256, 0, st>>>(
+            (long long)nslots0, dwpos.as<int>(), slotcol0.as<int>(), slotpb0.as<int>(), colptr, P.nzval.as<double>(),
             T.dump.as<double>(), T.slotcol.as<int>(), T.slotpb.as<int>(), T.slotptr.as<double *>());
         LAUNCHED(ctx);
         EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
@@ -1114,7 +1116,7 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
         TPRhsArgs A;
         A.nwarps = T.nctas * TP_MAXW; A.wdesc = T.wdesc.as<int4>(); A.slotcol = T.slotcol.as<int>(); A.slotpb = T.slotpb.as<int>();
         A.tmpl = T.tmpl.as<unsigned>(); A.fq = ctx->fq.as<double>(); A.Npad = T.Lg.Npad; A.nq = op.nq; A.b = bblk; A.overwrite = !accumulate;
-        const unsigned gr = nblocks((long long)T.nctas * TP_MAXW, 8);
+        const unsigned gr = nblocks((long long)T.nctas * TP_MAXW * TP_K, 8);
         if (op.nq == 1) tp_rhs_kernel<1><<<gr, 256, 0, ctx->stream>>>(A);
         else if (op.nq == 3) tp_rhs_kernel<3><<<gr, 256, 0, ctx->stream>>>(A);
         else if (op.nq == 4) tp_rhs_kernel<4><<<gr, 256, 0, ctx->stream>>>(A);
