@@ -106,6 +106,7 @@ struct Ctx {
     DevBuf custom_qw, custom_qx;
     DevBuf loc, bloc, sol, params_scratch, tab, geo, visit, fq;
     bool fast_enabled = true;   // option "fastpath"
+    bool nl_v2 = true;          // option "nonlinear_v2": 0 keeps the entry-wise local kernel of the nonlinear path
     bool tmpl_enabled = true;   // option "fastpath_templates": 0 keeps every column on the record kernel
     int tmpl_ahead = 1024;      // option "template_prefetch_ctas": CTAs ahead whose start-up data is prefetched into L2
     int tmpl_pool = TP_POOL_BYTES; // option "template_pool_bytes": shared-memory pool of one template CTA
@@ -1224,6 +1225,7 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     CTX_GUARD(ctx);
     if (key && !strcmp(key, "fastpath")) { C->fast_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_closed_form")) { C->bary_enabled = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "nonlinear_v2")) { C->nl_v2 = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_prefetch_ctas")) { C->tmpl_ahead = value < 0 ? 0 : value; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_pool_bytes")) { C->tmpl_pool = std::min(std::max(value, 4096), 200 * 1024); return EXTFEM_OK; }
@@ -1581,8 +1583,29 @@ int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc 
     if (int rc = ensure(C, C->loc, (size_t)op.ncells * op.NR * op.NC * 8)) return rc;
     if (int rc = ensure(C, C->bloc, (size_t)op.ncells * op.NR * 8)) return rc;
     EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[0], C->stream));
+    // combined operator vectors of v2 hold <= CVC_MAX entries per dof (all arguments on the dof's block together)
+    auto cv_entries = [&](const ArgDev *a, int n) {
+        int worst = 0;
+        for (int i = 0; i < n; ++i) {
+            int sum = 0;
+            for (int j = 0; j < n; ++j)
+                if (a[j].locoff == a[i].locoff) sum += a[j].op == EXTFEM_OP_ID ? 1 : (a[j].op == EXTFEM_OP_GRAD ? op.dim : (a[j].op == EXTFEM_OP_DIV ? 1 : op.dim));
+            worst = std::max(worst, sum);
+        }
+        return worst;
+    };
+    const bool v2 = C->nl_v2 && cv_entries(op.args, op.nargs) <= CVC_MAX && cv_entries(op.test, op.ntest) <= CVC_MAX && op.nin + op.nout <= 255;
     int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
         constexpr int DIM = decltype(dimc)::value;
+        if (v2) {
+            const size_t per_cell = nl2_cell_bytes((int)sizeof(CellGeo<DIM>), op.nq, op.nin, op.nout, op.NR, op.NC);
+            const int cpb = (int)std::max<size_t>(1, std::min<size_t>(8, (72 * 1024) / per_cell));
+            static bool attr_set = false;
+            if (!attr_set) { cudaFuncSetAttribute(local_nonlinear_kernel2<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+            local_nonlinear_kernel2<DIM><<<nblocks(op.ncells, cpb), 256, cpb * per_cell, C->stream>>>(op, C->loc.as<double>(),
+                                                                                                    C->bloc.as<double>(), cpb);
+            return;
+        }
         size_t per_cell = sizeof(CellGeo<DIM>) + (size_t)op.nq * (op.nout * op.nin + op.nout) * 8;
         int cpb = cells_per_block(per_cell);
         local_nonlinear_kernel<DIM><<<nblocks(op.ncells, cpb), 256, cpb * per_cell, C->stream>>>(op, C->loc.as<double>(),

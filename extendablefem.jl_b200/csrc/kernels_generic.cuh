@@ -548,6 +548,141 @@ local_nonlinear_kernel(const __grid_constant__ OpDev op, double *__restrict__ lo
     }
 }
 
+// ---- NonlinearOperator, restructured (v2) -------------------------------------------------------------
+// Same sums as local_nonlinear_kernel, organised as small dense contractions staged in shared memory:
+//   cvG/cvT   combined operator vectors of every local column / row dof at every quadrature point (all arguments that
+//             live on the dof's block: e.g. id(u) and grad(u)), evaluated ONCE per cell instead of once per local entry
+//   u, J, F   per quadrature point: input_args from cvG, kernel value and analytic Jacobian
+//   GJ        w_q * J_q * cvG   (nout values per column dof and point)
+//   A_loc     sum_q cvT . GJ    (<= 6 multiply-adds per point and entry), scaled by factor*|T| once per cell
+//             (nonlinear_operator.jl:396,419); rhs sum_q cvT . (J u - F) pre-scaled per point (:406)
+constexpr int CVC_MAX = 6;
+struct CVC {
+    double v[CVC_MAX];
+    unsigned char idx[CVC_MAX];
+    unsigned char len, pad;
+};
+
+template <int DIM>
+__device__ __forceinline__ void combined_cv(const ArgDev *args, int nargs, int loc, int q, const double *Ainv, double offdiag, CVC &out)
+{
+    int n = 0;
+    for (int i = 0; i < nargs; ++i) {
+        const ArgDev &a = args[i];
+        if (loc < a.locoff || loc >= a.locoff + a.nd) continue;
+        CV cv = eval_cv<DIM>(a, loc - a.locoff, q, Ainv, offdiag);
+        for (int t = 0; t < cv.len && n < CVC_MAX; ++t, ++n) { out.v[n] = cv.v[t]; out.idx[n] = (unsigned char)(a.opoff + cv.idx[t]); }
+    }
+    out.len = (unsigned char)n;
+}
+
+__host__ __device__ inline size_t nl2_cell_bytes(int sizeof_geo, int nq, int nin, int nout, int NR, int NC)
+{
+    size_t b = (size_t)sizeof_geo + (size_t)nq * nin * nout * 8 + (size_t)nq * nout * 8 + (size_t)nq * (NR + NC) * sizeof(CVC) +
+               (size_t)nq * NC * nout * 8;
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+local_nonlinear_kernel2(const __grid_constant__ OpDev op, double *__restrict__ loc, double *__restrict__ bloc, int CPB)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nin = op.nin, nout = op.nout, JS = nin * nout, nq = op.nq, NR = op.NR, NC = op.NC;
+    const size_t cb = nl2_cell_bytes((int)sizeof(CellGeo<DIM>), nq, nin, nout, NR, NC);
+    auto geo_of = [&](int s) { return reinterpret_cast<CellGeo<DIM> *>(smem_raw + s * cb); };
+    auto jq_of = [&](int s) { return reinterpret_cast<double *>(smem_raw + s * cb + sizeof(CellGeo<DIM>)); };   // [nq][nout][nin]
+    auto rq_of = [&](int s) { return jq_of(s) + (size_t)nq * JS; };                                              // [nq][nout]
+    auto gj_of = [&](int s) { return rq_of(s) + (size_t)nq * nout; };                                            // [nq][NC][nout]
+    auto cvg_of = [&](int s) { return reinterpret_cast<CVC *>(gj_of(s) + (size_t)nq * NC * nout); };             // [nq][NC]
+    auto cvt_of = [&](int s) { return cvg_of(s) + (size_t)nq * NC; };                                            // [nq][NR]
+    const long long c0 = (long long)blockIdx.x * CPB;
+    const int ncell = (int)min((long long)CPB, op.ncells - c0);
+    for (int s = threadIdx.x; s < ncell; s += blockDim.x) load_geo<DIM>(op, c0 + s, *geo_of(s));
+    __syncthreads();
+    // combined operator vectors
+    for (int e = threadIdx.x; e < ncell * nq * (NC + NR); e += blockDim.x) {
+        const int s = e / (nq * (NC + NR)), r = e - s * nq * (NC + NR);
+        const int q = r / (NC + NR), i = r - q * (NC + NR);
+        const CellGeo<DIM> &G = *geo_of(s);
+        if (i < NC) combined_cv<DIM>(op.args, op.nargs, i, q, G.Ainv, op.offdiag, cvg_of(s)[q * NC + i]);
+        else combined_cv<DIM>(op.test, op.ntest, i - NC, q, G.Ainv, op.offdiag, cvt_of(s)[q * NR + (i - NC)]);
+    }
+    __syncthreads();
+    // input_args, kernel value and Jacobian per quadrature point
+    for (int t = threadIdx.x; t < ncell * nq; t += blockDim.x) {
+        const int s = t / nq, q = t - s * nq;
+        const CellGeo<DIM> &G = *geo_of(s);
+        double u[MAXOP], val[MAXOP];
+        for (int d = 0; d < nin; ++d) u[d] = 0.0;
+        const CVC *cg = cvg_of(s) + q * NC;
+        for (int id = 0; id < op.nargs; ++id) {       // every column block once (arguments on one block share their dofs)
+            const ArgDev &a = op.args[id];
+            bool seen = false;
+            for (int i2 = 0; i2 < id; ++i2) seen |= (op.args[i2].locoff == a.locoff);
+            if (seen) continue;
+            const int *dofs = a.celldofs + (c0 + s) * a.nd;
+            for (int j = 0; j < a.nd; ++j) {
+                const double sv = op.sol[a.soloff + dofs[j]];
+                const CVC &c = cg[a.locoff + j];
+                for (int x = 0; x < c.len; ++x) u[c.idx[x]] += sv * c.v[x];
+            }
+        }
+        double *J = jq_of(s) + (size_t)q * JS;
+        nl_apply(op.kernel_id, DIM, u, op.params, val, J, nin, nout);
+        const double sc = op.factor * op.qw[q] * G.vol;
+        for (int k = 0; k < nout; ++k) {
+            double sum = 0.0;
+            for (int d = 0; d < nin; ++d) sum += J[k * nin + d] * u[d];
+            rq_of(s)[q * nout + k] = (sum - val[k]) * sc;
+        }
+    }
+    __syncthreads();
+    // GJ = w_q J_q cvG
+    for (int e = threadIdx.x; e < ncell * nq * NC * nout; e += blockDim.x) {
+        const int s = e / (nq * NC * nout), r = e - s * nq * NC * nout;
+        const int q = r / (NC * nout), r2 = r - q * NC * nout;
+        const int j = r2 / nout, t = r2 - j * nout;
+        const CVC &c = cvg_of(s)[q * NC + j];
+        const double *Jrow = jq_of(s) + (size_t)q * JS + t * nin;
+        double a = 0.0;
+        for (int x = 0; x < c.len; ++x) a += Jrow[c.idx[x]] * c.v[x];
+        gj_of(s)[r] = a * op.qw[q];
+    }
+    __syncthreads();
+    const int NRC = NR * NC;
+    for (int e = threadIdx.x; e < ncell * NRC; e += blockDim.x) {
+        const int s = e / NRC, r = e - s * NRC;
+        const int j = r / NR, k = r - j * NR;
+        const CellGeo<DIM> &G = *geo_of(s);
+        double acc = 0.0;
+        if (G.visited) {
+            const double *gj = gj_of(s) + (size_t)j * nout;
+            const CVC *ct = cvt_of(s) + k;
+            for (int q = 0; q < nq; ++q) {
+                const CVC &c = ct[q * NR];
+                const double *g = gj + (size_t)q * NC * nout;
+                for (int x = 0; x < c.len; ++x) acc += c.v[x] * g[c.idx[x]];
+            }
+            acc *= op.factor * G.vol;
+        }
+        loc[(size_t)(c0 + s) * NRC + r] = acc;
+    }
+    for (int e = threadIdx.x; e < ncell * NR; e += blockDim.x) {
+        const int s = e / NR, k = e - s * NR;
+        const CellGeo<DIM> &G = *geo_of(s);
+        double acc = 0.0;
+        if (G.visited) {
+            for (int q = 0; q < nq; ++q) {
+                const CVC &c = cvt_of(s)[q * NR + k];
+                const double *f = rq_of(s) + q * nout;
+                for (int x = 0; x < c.len; ++x) acc += f[c.idx[x]] * c.v[x];
+            }
+        }
+        bloc[(size_t)(c0 + s) * NR + k] = acc;
+    }
+}
+
 // x at quadrature points (extfem_quadrature_points)
 template <int DIM>
 __global__ void quadpoints_kernel(const __grid_constant__ OpDev op, double *__restrict__ xq)

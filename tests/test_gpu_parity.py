@@ -246,6 +246,35 @@ def test_nonlinear_2d_p2p1(pkg, ora, engine, kernel, params):
     check_values(res, bref - A @ sol, scale=max(np.abs(bref).max(), np.abs(nzref).max() * np.abs(sol).max()), what="residual")
 
 
+@pytest.mark.parametrize("case", ["nse2d", "neohooke3d"])
+def test_nonlinear_local_kernel_versions_agree(pkg, ora, engine, case):
+    """The staged-contraction local kernel (v2, default) and the entry-wise one are the same sums reassociated."""
+    if case == "nse2d":
+        g = pkg.uniform_refine(pkg.grid_unitsquare(), 3)
+        S = System(pkg, ora, engine, g, [pkg.H1P2(2, 2), pkg.H1P1(1)])
+        sol = _sol_252(S)
+        args = [(0, ID), (0, GRAD), (1, ID)]
+        desc = engine.make_opdesc(args, args=args, kernel_id=pkg.lib.kernel_id("nse2d"), params=[0.05], regions=(1,))
+    else:
+        g = grids(pkg, 3, 3)
+        g.cellregions[::3] = 2
+        S = System(pkg, ora, engine, g, [pkg.H1P2(3, 3)])
+        u = pkg.FEVector(S.FES)
+        pkg.interpolate(u[0], lambda x: 0.1 * np.stack([x[:, 0] ** 2, x[:, 0] + x[:, 1], x[:, 1] * x[:, 2]], axis=1))
+        sol = u.entries
+        args = [(0, GRAD)]
+        desc = engine.make_opdesc(args, args=args, kernel_id=pkg.lib.kernel_id("neohooke3d"), params=[3.8, 5.7], regions=(1,))
+    a2 = np.empty(S.rowval.size); b2 = np.empty(S.N); a1 = np.empty(S.rowval.size); b1 = np.empty(S.N)
+    engine.assemble_nonlinear(S.pat, desc, sol, nzval_out=a2, b_out=b2)
+    engine.set_option("nonlinear_v2", 0)
+    try:
+        engine.assemble_nonlinear(S.pat, desc, sol, nzval_out=a1, b_out=b1)
+    finally:
+        engine.set_option("nonlinear_v2", 1)
+    check_values(a2, a1, rtol=1e-13, what="jacobian v2 vs v1")
+    check_values(b2, b1, rtol=1e-13, scale=max(np.abs(b1).max(), np.abs(a1).max() * np.abs(sol).max()), what="rhs v2 vs v1")
+
+
 def test_nonlinear_equals_bilinear_for_linear_kernel(pkg, ora, engine):
     """test/test_nonlinear_operator.jl:29-49: Jacobian of a linear kernel == BilinearOperator matrix, < 1e-14."""
     g = pkg.uniform_refine(pkg.grid_unitsquare(), 2)
