@@ -258,30 +258,47 @@ def run_ours(args):
     return out
 
 
-def cpu_baseline(pkg, args, n_sample=None, steps=1):
-    """The CPU restatement (oracle, a port of the reference's loops; Julia is not installed) timed on
-    a bounded sample of the same workload: one thread, insertion into an existing CSC pattern."""
+def cpu_baseline(pkg, args, n_sample=None, steps=1, threads=None):
+    """The CPU restatement (oracle, a port of the reference's loops; Julia is not installed) timed on a bounded sample of
+    the same workload with all host threads: the sample grid is cut into one contiguous cell range per thread and every
+    thread assembles its range into its own matrix / vector (insertion into an existing CSC pattern) -- the scheme of the
+    reference's `parallel = true` path (thread-private parts per partition, bilinear_operator.jl:969-979)."""
+    import threading
     from oracle import oracle as ora
     ora.build()
     n = n_sample or args.cpu_n
+    T = threads or max(1, len(os.sched_getaffinity(0)))
     X = np.linspace(0, 1, n + 1)
     grid = pkg.simplexgrid(X, X, X)
     FES = pkg.FESpace(pkg.H1P2(1, 3), grid)
-    om = ora.Mesh(grid.coords, grid.cellnodes, grid.cellregions, grid.cellvolumes)
-    gr = ora.OraArg(FES.celldofs, 1, 2, ora.OP_GRAD)
-    idu = ora.OraArg(FES.celldofs, 1, 2, ora.OP_ID)
-    colptr, rowval = ora.structural_pattern([gr], [gr], (FES.ndofs, FES.ndofs))
+    parts = []
+    for lo, hi in pkg.cell_ranges(grid.ncells, T):
+        sh = pkg.Shard(grid.coords, grid.cellnodes, grid.cellregions, FES.celldofs, lo, hi, order=2)
+        om = ora.Mesh(sh.coords, sh.cellnodes, sh.cellregions, np.ascontiguousarray(grid.cellvolumes[lo:hi]))
+        gr = ora.OraArg(sh.celldofs, 1, 2, ora.OP_GRAD)
+        idu = ora.OraArg(sh.celldofs, 1, 2, ora.OP_ID)
+        colptr, rowval = ora.structural_pattern([gr], [gr], (sh.ndofs, sh.ndofs))
+        parts.append((om, gr, idu, colptr, rowval, sh.ndofs))
+
+    def work(p):
+        om, gr, idu, colptr, rowval, nd = p
+        ora.assemble_bilinear(om, [gr], [gr], "standard", csc=(colptr, rowval))
+        b = np.zeros(nd)
+        ora.assemble_linear(om, [idu], b, "sincos301", params=[1.0])
+
     times = []
     for _ in range(steps):
+        th = [threading.Thread(target=work, args=(p,)) for p in parts]
         t0 = time.perf_counter()
-        ora.assemble_bilinear(om, [gr], [gr], "standard", csc=(colptr, rowval))
-        b = np.zeros(FES.ndofs)
-        ora.assemble_linear(om, [idu], b, "sincos301", params=[1.0])
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
         times.append(time.perf_counter() - t0)
     dt = float(np.mean(times))
-    return {"value": grid.ncells / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"same operators on simplexgrid n={n} ({grid.ncells} tets), C restatement of the reference loops "
-                      f"(gcc -O2, 1 thread), {dt:.2f} s per step; the Julia reference is not installable offline",
+    return {"value": grid.ncells / dt, "unit": UNIT, "cores": T, "kind": "port",
+            "sample": f"same operators on simplexgrid n={n} ({grid.ncells} tets) cut into {T} cell ranges, one thread each, C "
+                      f"restatement of the reference loops (gcc -O2), {dt:.2f} s per step; the Julia reference is not installable offline",
             "seconds_per_step": dt}
 
 
