@@ -30,6 +30,7 @@ struct Mesh {
     long long ncells = 0, nnodes = 0;
     DevBuf coords, cellnodes, regions, vol, geo;
     bool geo_valid = false;
+    long long vol_version = 0;       // bumped when the cell volumes change
 };
 
 struct Space {
@@ -52,10 +53,12 @@ struct FastPlan {
 // template plan of one diagonal block (fastplan.cuh)
 struct TemplatePlan {
     bool ready = false;
-    GeoLayout Lg{0, 1, 0, 0};
+    GeoLayout Lg{0, 0, 1, 0, 0};
     int nwarps = 0, nctas = 0, ngroups = 0, ntemplates = 0, pool_bytes = 0;
     long long nrounds = 0, nleft = 0, ncols = 0;
     DevBuf wdesc, slotcol, slotpb, slotptr, tmpl, leftcols, dump;
+    DevBuf cn_p, reg_p, vol_p;       // mesh arrays in the transposed cell order (Lg.permuted)
+    long long vol_version = -1;
 };
 
 struct Pattern {
@@ -110,6 +113,7 @@ struct Ctx {
     bool tmpl_enabled = true;   // option "fastpath_templates": 0 keeps every column on the record kernel
     int tmpl_ahead = 1024;      // option "template_prefetch_ctas": CTAs ahead whose start-up data is prefetched into L2
     int tmpl_pool = TP_POOL_BYTES; // option "template_pool_bytes": shared-memory pool of one template CTA
+    bool tmpl_permute_mesh = true; // option "template_permute_mesh": cell kernels read mesh copies in the transposed order
     int tmpl_mincols = 24;      // option "template_min_cols": smallest group of columns that gets a template
     bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator
     long long launches = 0;
@@ -548,11 +552,11 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     Mesh &M = *ctx->meshes[S.mesh];
     const long long ncols = S.ndofs;
     T.ncols = ncols;
-    T.Lg = GeoLayout{0, 1, M.ncells, M.ncells};
+    T.Lg = GeoLayout{0, 0, 1, M.ncells, M.ncells};
     cudaStream_t st = ctx->stream;
     auto all_left = [&]() -> int { // no templates: every column goes to the record kernel, geometry stays [cell][NG]
         T.nwarps = T.nctas = T.ntemplates = 0;
-        T.Lg = GeoLayout{0, 1, M.ncells, M.ncells};
+        T.Lg = GeoLayout{0, 0, 1, M.ncells, M.ncells};
         if (int rc = ensure(ctx, T.leftcols, (size_t)ncols * 4)) return rc;
         tp_iota_kernel<<<nblocks(ncols, 256), 256, 0, st>>>(ncols, T.leftcols.as<int>());
         LAUNCHED(ctx);
@@ -594,7 +598,7 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     for (int d = 1; d <= 64; ++d) if (hh[d] > hh[Pp]) Pp = d;
     if (hh[Pp] == 0) Pp = 1;
     GeoLayout Lg;
-    Lg.soa = 1; Lg.P = Pp; Lg.N = (M.ncells + Pp - 1) / Pp; Lg.Npad = Lg.N * Pp;
+    Lg.soa = 1; Lg.permuted = 0; Lg.P = Pp; Lg.N = (M.ncells + Pp - 1) / Pp; Lg.Npad = Lg.N * Pp;
     // final signature includes the residue of the base cell modulo P
     tp_key2_kernel<<<gb, 256, 0, st>>>(ncols, Pp, hash.as<unsigned long long>(), base.as<int>(), key.as<unsigned long long>(), col.as<int>());
     LAUNCHED(ctx);
@@ -755,6 +759,19 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     T.nrounds = nrounds;
     T.pool_bytes = pool * 8;
     T.Lg = Lg;
+    if (Lg.P > 1 && ctx->tmpl_permute_mesh) {
+        const int nv = M.dim + 1;
+        if (int rc = ensure(ctx, T.cn_p, (size_t)Lg.Npad * nv * 4)) return rc;
+        if (int rc = ensure(ctx, T.reg_p, (size_t)Lg.Npad * 4)) return rc;
+        if (int rc = ensure(ctx, T.vol_p, (size_t)Lg.Npad * 8)) return rc;
+        const unsigned gp = nblocks(Lg.Npad, 256);
+        if (nv == 2) tp_permute_mesh_kernel<2><<<gp, 256, 0, st>>>(Lg, M.ncells, M.cellnodes.as<int>(), M.regions.as<int>(), T.cn_p.as<int>(), T.reg_p.as<int>());
+        else if (nv == 3) tp_permute_mesh_kernel<3><<<gp, 256, 0, st>>>(Lg, M.ncells, M.cellnodes.as<int>(), M.regions.as<int>(), T.cn_p.as<int>(), T.reg_p.as<int>());
+        else tp_permute_mesh_kernel<4><<<gp, 256, 0, st>>>(Lg, M.ncells, M.cellnodes.as<int>(), M.regions.as<int>(), T.cn_p.as<int>(), T.reg_p.as<int>());
+        LAUNCHED(ctx);
+        T.Lg.permuted = 1;
+        T.vol_version = -1;
+    }
     {
         std::vector<int> hnw((size_t)ngroups);
         EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hnw.data(), gnw.p, (size_t)ngroups * 4, cudaMemcpyDeviceToHost));
@@ -847,6 +864,17 @@ static int build_fast_plan(Ctx *ctx, Pattern &P, int b, int ns)
     return 0;
 }
 
+// transposed-order copy of the cell volumes, refreshed when the mesh's volumes changed
+static int refresh_permuted_volumes(Ctx *ctx, Mesh &M, TemplatePlan &T)
+{
+    if (!T.Lg.permuted || T.vol_version == M.vol_version) return 0;
+    tp_permute_vol_kernel<<<nblocks(T.Lg.Npad, 256), 256, 0, ctx->stream>>>(T.Lg, M.ncells, M.vol.as<double>(), T.vol_p.as<double>());
+    LAUNCHED(ctx);
+    EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+    T.vol_version = M.vol_version;
+    return 0;
+}
+
 template <class EV, bool FIRST>
 static int launch_template(Ctx *ctx, Pattern &P, TemplatePlan &T, int b, int accumulate)
 {
@@ -876,9 +904,11 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
     Mesh &M = *R.mesh;
     if (int rc = ensure(ctx, ctx->geo, (size_t)(SOA ? T.Lg.Npad : M.ncells) * NG * 8)) return rc;
     if (d->nregions > 0) if (int rc = upload(ctx, ctx->visit, d->regions, (size_t)d->nregions * 4)) return rc;
-    fp_geo_kernel<DIM, GEO, SOA><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(
-        M.ncells, M.coords.as<double>(), M.cellnodes.as<int>(), M.regions.as<int>(), M.vol.as<double>(), d->factor * geoscale,
-        d->nregions, ctx->visit.as<int>(), ctx->geo.as<double>(), T.Lg);
+    if (int rc = refresh_permuted_volumes(ctx, M, T)) return rc;
+    const bool perm = SOA && T.Lg.permuted;
+    fp_geo_kernel<DIM, GEO, SOA><<<nblocks(perm ? T.Lg.Npad : M.ncells, 256), 256, 0, ctx->stream>>>(
+        M.ncells, M.coords.as<double>(), perm ? T.cn_p.as<int>() : M.cellnodes.as<int>(), perm ? T.reg_p.as<int>() : M.regions.as<int>(),
+        perm ? T.vol_p.as<double>() : M.vol.as<double>(), d->factor * geoscale, d->nregions, ctx->visit.as<int>(), ctx->geo.as<double>(), T.Lg);
     LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (SOA && T.nwarps > 0) {
@@ -1102,15 +1132,19 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
     }
     RhsCellArgs C;
     memset(&C, 0, sizeof(C));
-    C.ncells = M.ncells; C.coords = M.coords.as<double>(); C.cellnodes = M.cellnodes.as<int>(); C.regions = M.regions.as<int>();
-    C.vol = M.vol.as<double>(); C.qw = op.qw; C.qx = op.qx; C.tabulated = op.tabulated; C.nq = op.nq; C.kernel_id = op.kernel_id;
+    if (int rc = refresh_permuted_volumes(ctx, M, T)) return rc;
+    const bool perm = T.Lg.permuted != 0;
+    C.ncells = M.ncells; C.coords = M.coords.as<double>(); C.cellnodes = perm ? T.cn_p.as<int>() : M.cellnodes.as<int>();
+    C.regions = perm ? T.reg_p.as<int>() : M.regions.as<int>();
+    C.vol = perm ? T.vol_p.as<double>() : M.vol.as<double>(); C.qw = op.qw; C.qx = op.qx; C.tabulated = op.tabulated; C.nq = op.nq; C.kernel_id = op.kernel_id;
     C.nregions = op.nregions;
     for (int i = 0; i < op.nregions; ++i) C.visit[i] = op.regions[i];
     for (int i = 0; i < op.nparams; ++i) C.params[i] = op.params[i];
     C.factor = op.factor; C.Lg = T.Lg; C.fq = ctx->fq.as<double>();
-    if (dim == 1) tp_rhs_cell_kernel<1><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(C);
-    else if (dim == 2) tp_rhs_cell_kernel<2><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(C);
-    else tp_rhs_cell_kernel<3><<<nblocks(M.ncells, 256), 256, 0, ctx->stream>>>(C);
+    const unsigned gcell = nblocks(perm ? T.Lg.Npad : M.ncells, 256);
+    if (dim == 1) tp_rhs_cell_kernel<1><<<gcell, 256, 0, ctx->stream>>>(C);
+    else if (dim == 2) tp_rhs_cell_kernel<2><<<gcell, 256, 0, ctx->stream>>>(C);
+    else tp_rhs_cell_kernel<3><<<gcell, 256, 0, ctx->stream>>>(C);
     LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (T.nwarps > 0) {
@@ -1229,6 +1263,7 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_prefetch_ctas")) { C->tmpl_ahead = value < 0 ? 0 : value; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_pool_bytes")) { C->tmpl_pool = std::min(std::max(value, 4096), 200 * 1024); return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_permute_mesh")) { C->tmpl_permute_mesh = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_min_cols")) { C->tmpl_mincols = value < 1 ? 1 : value; return EXTFEM_OK; }
     return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("unknown option ") + (key ? key : "(null)"));
 }
@@ -1303,6 +1338,7 @@ int extfem_mesh_update_coords(extfem_ctx *ctx, int mesh, const double *coords, c
         LAUNCHED(C);
     }
     M.geo_valid = false;
+    ++M.vol_version;
     return EXTFEM_OK;
 }
 

@@ -35,6 +35,7 @@ namespace extfem {
 // layout of the per-cell scratch records (geometry, RHS point values)
 struct GeoLayout {
     int soa;            // 0: array of structures [cell][NG]; 1: [g][Npad] in period-P transposed cell order
+    int permuted;       // the cell kernels read mesh arrays that were copied into the transposed order
     int P;              // period (1: identity)
     long long N, Npad;  // N = ceil(ncells / P), Npad = N * P
 };
@@ -181,8 +182,11 @@ fp_geo_kernel(long long ncells, const double *__restrict__ coords, const int *__
               const int *__restrict__ regions, const double *__restrict__ vol, double factor, int nregions,
               const int *__restrict__ visit /* device copy of regions list */, double *__restrict__ geo, const GeoLayout Lg)
 {
+    // SOA with Lg.permuted: cellnodes / regions / vol are copies in the transposed cell order (fastplan: tp_permute_*), the
+    // thread index IS the transposed index: every load and store of the kernel is coalesced
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncells) return;
+    if (c >= (SOA && Lg.permuted ? Lg.Npad : ncells)) return;
+    if (SOA && Lg.permuted && cellnodes[c * (DIM + 1)] < 0) return;   // padding slot of the transposed order
     constexpr int NG = fp_ng(DIM, GEO);
     double f = factor * vol[c];
     if (nregions > 0) {
@@ -190,7 +194,7 @@ fp_geo_kernel(long long ncells, const double *__restrict__ coords, const int *__
         for (int k = 0; k < nregions; ++k) vis |= (visit[k] == reg);
         if (!vis) f = 0.0;
     }
-    double *g = SOA ? geo + geo_perm(Lg, c) : geo + c * NG;
+    double *g = SOA ? geo + (Lg.permuted ? c : geo_perm(Lg, c)) : geo + c * NG;
     if (GEO == FP_GEO_VOLUME) { g[0] = f; return; }
     int cn[DIM + 1];
     if (DIM == 3) {

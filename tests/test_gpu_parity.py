@@ -105,6 +105,15 @@ def test_template_path(pkg, ora, engine, dim, order, n):
                 finally:
                     engine.set_option("fastpath", 1)
                 check_values(a, b, rtol=1e-13, what="template vs generic")
+        # moving mesh: new coordinates (x2) refresh the transposed-order volume copy; mass scales by 2^dim
+        dmass = engine.make_opdesc([(0, ID)], [(0, ID)], factor=0.75)
+        refm = ora.assemble_bilinear(S.omesh, S.oargs([(0, ID)]), S.oargs([(0, ID)]), factor=0.75, csc=(S.colptr, S.rowval))
+        engine.mesh_update_coords(S.mesh, np.ascontiguousarray(2.0 * g.coords))
+        engine.assemble_bilinear(S.pat, dmass, nzval_out=a)
+        check_values(a, 2.0 ** dim * refm, what="template mass after coordinate update")
+        engine.mesh_update_coords(S.mesh, g.coords, g.cellvolumes)
+        engine.assemble_bilinear(S.pat, dmass, nzval_out=a)
+        check_values(a, refm, what="template mass after restoring coordinates")
         # the same system with templates switched off: record kernel only, identical sums
         engine.set_option("fastpath_templates", 0)
         try:
