@@ -223,6 +223,13 @@ def run_ours(args):
             pass
         peak = peaks.get("hbm_gbs", 6650.0)
         alg = algorithmic_bytes(grid, FES, nnz)
+        traffic = None      # ncu dram__bytes_read.sum + dram__bytes_write.sum of the stiffness kernels (committed capture)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_f_traffic.json")))
+            if tj.get("workload") == f"n={args.n}":
+                traffic = tj["stiffness_dram_bytes_per_assembly"]
+        except Exception:
+            pass
         dom_ms = kern_ms[0] + kern_ms[1]          # local + gather kernels of the stiffness assembly
         achieved = alg / (dom_ms * 1e-3) / 1e9
         out = {
@@ -236,7 +243,8 @@ def run_ours(args):
                                        if world > 1 else "1 GPU")},
             "nnz_per_s": nnz * world / (ms_step * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "traffic": traffic, "traffic_source": "ncu capture profiles/r01_f_final_ncu_summary.txt" if traffic else None,
+                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "kernel": "stiffness assembly kernels (local + gather)", "kernel_ms": dom_ms,
                          "algorithmic_bytes": alg, "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
