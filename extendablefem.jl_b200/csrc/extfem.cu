@@ -113,6 +113,8 @@ struct Ctx {
     bool tmpl_enabled = true;   // option "fastpath_templates": 0 keeps every column on the record kernel
     int tmpl_ahead = 1024;      // option "template_prefetch_ctas": CTAs ahead whose start-up data is prefetched into L2
     int tmpl_pool = TP_POOL_BYTES; // option "template_pool_bytes": shared-memory pool of one template CTA
+    bool tmpl_const = true;     // option "template_constant_memory": template rounds in constant memory when they fit
+    const void *const_tmpl_owner = nullptr;
     bool tmpl_permute_mesh = true; // option "template_permute_mesh": cell kernels read mesh copies in the transposed order
     int tmpl_mincols = 24;      // option "template_min_cols": smallest group of columns that gets a template
     bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator
@@ -779,6 +781,9 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
         for (int g = 0; g < ngroups; ++g) T.ntemplates += hnw[g] > 0;
     }
     if (int rc = upload(ctx, T.wdesc, launch.data(), launch.size() * 16)) return rc;
+    tp_affine_kernel<<<nblocks((long long)launch.size(), 8), 256, 0, st>>>((int)launch.size(), T.slotcol.as<int>(), T.slotptr.as<double *>(),
+                                                                         T.wdesc.as<int4>());
+    LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
     EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
     return 0;
@@ -875,7 +880,7 @@ static int refresh_permuted_volumes(Ctx *ctx, Mesh &M, TemplatePlan &T)
     return 0;
 }
 
-template <class EV, bool FIRST>
+template <class EV, bool FIRST, bool CT>
 static int launch_template(Ctx *ctx, Pattern &P, TemplatePlan &T, int b, int accumulate)
 {
     TPArgs A;
@@ -883,7 +888,7 @@ static int launch_template(Ctx *ctx, Pattern &P, TemplatePlan &T, int b, int acc
     A.tmpl = T.tmpl.as<unsigned>(); A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
     A.nwarps = T.nctas * TP_MAXW; A.ahead = ctx->tmpl_ahead * TP_MAXW;
     (void)P; (void)b;
-    auto k = tp_gather_kernel<EV, FIRST>;
+    auto k = tp_gather_kernel<EV, FIRST, CT>;
     static bool attr_set = false;
     if (!attr_set) {
         EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -914,8 +919,16 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
     if (SOA && T.nwarps > 0) {
         // first-touch stores need: overwrite, and column segments that hold rows of this block only
         const bool first = !accumulate && P.rowspaces.size() == 1;
-        if (int rc = first ? launch_template<EV, true>(ctx, P, T, b, accumulate) : launch_template<EV, false>(ctx, P, T, b, accumulate))
-            return rc;
+        // templates in constant memory when they fit (re-uploaded when another plan used the bank in between)
+        const bool ct = ctx->tmpl_const && T.nrounds <= TP_CONST_ROUNDS;
+        if (ct && ctx->const_tmpl_owner != &T) {
+            EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_tmpl, T.tmpl.p, (size_t)T.nrounds * TP_TW * 4, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+            ctx->const_tmpl_owner = &T;
+        }
+        int rc;
+        if (ct) rc = first ? launch_template<EV, true, true>(ctx, P, T, b, accumulate) : launch_template<EV, false, true>(ctx, P, T, b, accumulate);
+        else rc = first ? launch_template<EV, true, false>(ctx, P, T, b, accumulate) : launch_template<EV, false, false>(ctx, P, T, b, accumulate);
+        if (rc) return rc;
     }
     if (F.nchunks > 0) {
         FastArgs A;
@@ -1263,6 +1276,7 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_prefetch_ctas")) { C->tmpl_ahead = value < 0 ? 0 : value; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_pool_bytes")) { C->tmpl_pool = std::min(std::max(value, 4096), 200 * 1024); return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_constant_memory")) { C->tmpl_const = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_permute_mesh")) { C->tmpl_permute_mesh = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_min_cols")) { C->tmpl_mincols = value < 1 ? 1 : value; return EXTFEM_OK; }
     return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("unknown option ") + (key ? key : "(null)"));
