@@ -672,7 +672,7 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
     if (int rc = ensure(ctx, nsel, 8)) return rc;
     EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(slotcol0.p, 0xff, nslots0 * 4, st));
     EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(slotpb0.p, 0, nslots0 * 4, st));
-    tp_tmpl_kernel<<<nblocks(ngroups, 128), 128, 0, st>>>(ngroups, ns, posstride, Lg, gstart.as<int>(), order.as<int>(), gnr.as<long long>(),
+    tp_tmpl_kernel<<<nblocks(ngroups, 128), 128, 0, st>>>(ngroups, ns, posstride, M.dim, S.order, Lg, gstart.as<int>(), order.as<int>(), gnr.as<long long>(),
                                                           gr0.as<long long>(), adjptr, adjcell, adjloc, posmap, T.tmpl.as<unsigned>());
     LAUNCHED(ctx);
     tp_slot_kernel<<<gb, 256, 0, st>>>(ncols, Lg, order.as<int>(), gid1.as<int>(), gstart.as<int>(), gnw.as<int>(), gw0.as<int>(),

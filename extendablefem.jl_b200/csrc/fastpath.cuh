@@ -301,6 +301,10 @@ struct FastArgs {
 template <int NS_, int NG_, int NV_>
 struct EvalTable {
     static constexpr int NS = NS_, NG = NG_, NV = NV_;
+    // rows that EVERY adjacent cell of a column contributes to can be accumulated in registers (fastplan: template kernel):
+    // slot of local row t for a column with local index kl, -1: none.  Any element: the column dof itself.
+    static constexpr int NCOMMON = 1;
+    __host__ __device__ static constexpr int common_slot(int kl, int t) { return t == kl ? 0 : -1; }
     template <int KL, int T0, int T1>
     __device__ __forceinline__ static void column(const double (&G)[NG], double (&cur)[NS])
     {
@@ -317,6 +321,17 @@ struct EvalTable {
 template <int DIM, int ORDER>
 struct EvalBary {
     static constexpr int NV = DIM + 1, NS = ORDER == 1 ? DIM + 1 : (DIM + 1) * (DIM + 2) / 2, NG = DIM * (DIM + 1) / 2;
+    // P2: every cell around an edge dof also holds the edge's two end points: slots 1 / 2 (local edge vertices a / b)
+    static constexpr int NCOMMON = ORDER == 2 ? 3 : 1;
+    __host__ __device__ static constexpr int common_slot(int kl, int t)
+    {
+        if (t == kl) return 0;
+        if (ORDER == 2 && kl >= NV) {
+            if (t == fp_edge_a<DIM>(kl - NV)) return 1;
+            if (t == fp_edge_b<DIM>(kl - NV)) return 2;
+        }
+        return -1;
+    }
     template <int KL, int T0, int T1>
     __device__ __forceinline__ static void column(const double (&G)[NG], double (&cur)[NS])
     {

@@ -75,14 +75,24 @@ def test_fastpath_equals_generic(pkg, ora, engine, dim, order):
             check_values(b, ref, what="fast (table evaluator) vs oracle")
 
 
-@pytest.mark.parametrize("dim,order,n", [(3, 2, 7), (3, 1, 8), (2, 2, 12), (2, 1, 12)])
-def test_template_path(pkg, ora, engine, dim, order, n):
+@pytest.mark.parametrize("dim,order,n,permute", [(3, 2, 7, False), (3, 1, 8, False), (2, 2, 12, False), (2, 1, 12, False),
+                                                 (3, 2, 7, True), (2, 2, 12, True)])
+def test_template_path(pkg, ora, engine, dim, order, n, permute):
     """Template (dictionary-compressed scatter map) kernels: structured grid, templates forced for small groups so that
     nearly every column runs on the template kernel; first-touch and accumulate modes; against the record kernel
     (templates off), the generic path and the oracle; the fast RHS on the same plan."""
     X = np.linspace(0, 1, n + 1)
     g = pkg.simplexgrid(*([X] * dim))
     g.cellregions[1::5] = 2
+    if permute:
+        # even permutations of the local vertex order (orientation kept) that differ between neighbouring cells: the local
+        # edge end points (a, b) of a P2 edge dof then map to its two global vertices in either order (register-row swap)
+        cn = g.cellnodes.copy()
+        for k, p in ((1, [1, 2, 0]), (2, [2, 0, 1])):
+            sel = np.arange(g.ncells) % 3 == k
+            cn[sel, :3] = g.cellnodes[sel][:, p]
+        g.cellnodes[:] = cn
+        g._cache.clear()
     engine.set_option("template_min_cols", 2)
     try:
         S = System(pkg, ora, engine, g, [pkg.H1Pk(1, dim, order)])
