@@ -109,7 +109,8 @@ struct Ctx {
     DevBuf custom_qw, custom_qx;
     DevBuf loc, bloc, sol, params_scratch, tab, geo, visit, fq;
     bool fast_enabled = true;   // option "fastpath"
-    bool nl_v2 = true;          // option "nonlinear_v2": 0 keeps the entry-wise local kernel of the nonlinear path
+    int nl_version = 3;         // option "nonlinear_kernel": 1 entry-wise local kernel, 2 staged per block, 3 warp per cell
+    DevBuf nl2buf;
     bool tmpl_enabled = true;   // option "fastpath_templates": 0 keeps every column on the record kernel
     int tmpl_ahead = 1024;      // option "template_prefetch_ctas": CTAs ahead whose start-up data is prefetched into L2
     int tmpl_pool = TP_POOL_BYTES; // option "template_pool_bytes": shared-memory pool of one template CTA
@@ -1106,6 +1107,122 @@ static int try_fast_bilinear(Ctx *ctx, Pattern &P, const Prepared &R, const extf
     return 0;
 }
 
+// host tables of the warp-per-cell nonlinear local kernel (kernels_generic.cuh: local_nonlinear_kernel3)
+struct NL3Dof { int n = 0, space = 0, scalar = 0; int out[CVC_MAX], src[CVC_MAX]; double scale[CVC_MAX]; };
+
+static bool nl3_dofops(const ArgDev *args, int nargs, int dim, double offdiag, int loc, const std::vector<const double *> &spaces, NL3Dof &D)
+{
+    int n = 0;
+    for (int i = 0; i < nargs; ++i) {
+        const ArgDev &a = args[i];
+        if (loc < a.locoff || loc >= a.locoff + a.nd) continue;
+        const int jj = loc - a.locoff, c = jj / a.nscalar, k = jj % a.nscalar;
+        int sp = 0;
+        while (sp < (int)spaces.size() && spaces[sp] != a.refvals) ++sp;
+        if (n > 0 && (D.space != sp || D.scalar != k)) return false;   // arguments on one block must share the space
+        D.space = sp; D.scalar = k;
+        auto add = [&](int out, int src, double scale) { if (n < CVC_MAX) { D.out[n] = a.opoff + out; D.src[n] = src; D.scale[n] = scale; } ++n; };
+        switch (a.op) {
+        case EXTFEM_OP_ID: add(c, 0, 1.0); break;
+        case EXTFEM_OP_GRAD: for (int d = 0; d < dim; ++d) add(c * dim + d, 1 + d, 1.0); break;
+        case EXTFEM_OP_DIV: add(0, 1 + (c < dim ? c : 0), 1.0); break;
+        default: // SYMGRAD_VOIGT, mirrors eval_cv
+            if (dim == 1) add(0, 1, 1.0);
+            else if (dim == 2) { add(c, 1 + c, 1.0); add(2, 1 + ((1 - c) & 1), offdiag); }
+            else {
+                const int o1 = (c == 0) ? 4 : 3, o2 = (c == 2) ? 4 : 5, g1 = (c == 0) ? 2 : ((c == 1) ? 2 : 1), g2 = (c == 0) ? 1 : 0;
+                add(c, 1 + c, 1.0); add(o1, 1 + g1, offdiag); add(o2, 1 + g2, offdiag);
+            }
+        }
+    }
+    D.n = n;
+    return n <= CVC_MAX;
+}
+
+static int build_nl3_tables(Ctx *ctx, const OpDev &op, NL3Tables &T, bool *ok)
+{
+    *ok = false;
+    memset(&T, 0, sizeof(T));
+    if (op.NR > 255 || op.NC > 255 || op.nin > 255 || op.nout > 255 || op.nq > 255) return 0;
+    std::vector<const double *> spaces, sgrads;
+    std::vector<int> sns;
+    auto note = [&](const ArgDev &a) {
+        for (auto p : spaces) if (p == a.refvals) return;
+        spaces.push_back(a.refvals); sgrads.push_back(a.refgrads); sns.push_back(a.nscalar);
+    };
+    for (int i = 0; i < op.nargs; ++i) note(op.args[i]);
+    for (int i = 0; i < op.ntest; ++i) note(op.test[i]);
+    if ((int)spaces.size() > NL2_MAXSP_) return 0;
+    std::vector<NL3Dof> cols(op.NC), rows(op.NR);
+    for (int j = 0; j < op.NC; ++j) if (!nl3_dofops(op.args, op.nargs, op.dim, op.offdiag, j, spaces, cols[j])) return 0;
+    for (int k = 0; k < op.NR; ++k) if (!nl3_dofops(op.test, op.ntest, op.dim, op.offdiag, k, spaces, rows[k])) return 0;
+    std::vector<int> phi_off;
+    int off = 0;
+    for (size_t s = 0; s < spaces.size(); ++s) { phi_off.push_back(off); off += op.nq * sns[s] * (1 + op.dim); }
+    bool same = op.NC == op.NR;
+    for (int j = 0; same && j < op.NC; ++j) {
+        same = cols[j].n == rows[j].n && cols[j].space == rows[j].space && cols[j].scalar == rows[j].scalar;
+        for (int x = 0; same && x < cols[j].n; ++x)
+            same = cols[j].out[x] == rows[j].out[x] && cols[j].src[x] == rows[j].src[x] && cols[j].scale[x] == rows[j].scale[x];
+    }
+    std::vector<unsigned char> host;
+    auto reserve = [&](size_t bytes) { size_t o = (host.size() + 15) / 16 * 16; host.resize(o + bytes, 0); return (int)o; };
+    auto pack = [&](const std::vector<NL3Dof> &D, int N, int &E, int &o_n, int &o_out, int &o_idx, int &o_sc) {
+        E = 1;
+        for (int i = 0; i < N; ++i) E = std::max(E, D[i].n);
+        o_n = reserve(N);
+        o_out = reserve((size_t)E * N);
+        o_idx = reserve((size_t)op.nq * E * N * 4);
+        o_sc = reserve((size_t)op.nq * E * N * 8);
+        for (int i = 0; i < N; ++i) {
+            host[o_n + i] = (unsigned char)D[i].n;
+            for (int x = 0; x < E; ++x) {
+                host[o_out + (size_t)x * N + i] = x < D[i].n ? (unsigned char)D[i].out[x] : 0;
+                for (int q = 0; q < op.nq; ++q) {
+                    const size_t it = ((size_t)q * E + x) * N + i;
+                    reinterpret_cast<int *>(host.data() + o_idx)[it] =
+                        x < D[i].n ? phi_off[D[i].space] + (q * sns[D[i].space] + D[i].scalar) * (1 + op.dim) + D[i].src[x] : -1;
+                    reinterpret_cast<double *>(host.data() + o_sc)[it] = x < D[i].n ? D[i].scale[x] : 0.0;
+                }
+            }
+        }
+    };
+    T.NC = op.NC; T.NR = op.NR; T.same = same ? 1 : 0;
+    pack(cols, op.NC, T.EC, T.o_cn, T.o_cout, T.o_bgidx, T.o_bgsc);
+    if (same) { T.ER = T.EC; T.o_rn = T.o_cn; T.o_rout = T.o_cout; T.o_btidx = T.o_bgidx; T.o_btsc = T.o_bgsc; }
+    else pack(rows, op.NR, T.ER, T.o_rn, T.o_rout, T.o_btidx, T.o_btsc);
+    T.o_gj = reserve((size_t)op.nq * op.NC * op.nout * 4);
+    {
+        unsigned *gj = reinterpret_cast<unsigned *>(host.data() + T.o_gj);
+        size_t i = 0;
+        for (int q = 0; q < op.nq; ++q)
+            for (int j = 0; j < op.NC; ++j)
+                for (int t = 0; t < op.nout; ++t) gj[i++] = (unsigned)q | ((unsigned)j << 8) | ((unsigned)t << 16);
+    }
+    T.o_ent = reserve((size_t)op.NR * op.NC * 2);
+    for (int j = 0; j < op.NC; ++j)
+        for (int k = 0; k < op.NR; ++k) reinterpret_cast<unsigned short *>(host.data() + T.o_ent)[(size_t)j * op.NR + k] = (unsigned short)(j | (k << 8));
+    reserve(0);
+    host.resize((host.size() + 15) / 16 * 16, 0);
+    T.tab_bytes = (int)host.size();
+    if (int rc = upload(ctx, ctx->nl2buf, host.data(), host.size())) return rc;
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    T.tab = ctx->nl2buf.as<unsigned char>();
+    T.nspaces = (int)spaces.size();
+    for (int s = 0; s < T.nspaces; ++s) { T.ns[s] = sns[s]; T.refvals[s] = spaces[s]; T.refgrads[s] = sgrads[s]; T.phi_off[s] = phi_off[s]; }
+    T.phi_off[T.nspaces] = off;
+    for (int i = 0; i < op.nargs; ++i) {
+        bool seen = false;
+        for (int b = 0; b < T.ncolblocks; ++b) seen |= T.blk_locoff[b] == op.args[i].locoff;
+        if (seen) continue;
+        const int b = T.ncolblocks++;
+        T.blk_locoff[b] = op.args[i].locoff; T.blk_nd[b] = op.args[i].nd; T.blk_celldofs[b] = op.args[i].celldofs;
+        T.blk_soloff[b] = op.args[i].soloff;
+    }
+    *ok = true;
+    return 0;
+}
+
 // fast right-hand side: LinearOperator(f, [id(u)]) on a scalar P1/P2 space (linear_operator.jl:584-640).  Per cell the
 // point values factor*w_q*|T|*f(x_q) (structure-of-arrays, geometry order), per dof an owner-computes sum over the
 // adjacent cells driven by the template plan of the block.
@@ -1272,7 +1389,8 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     CTX_GUARD(ctx);
     if (key && !strcmp(key, "fastpath")) { C->fast_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_closed_form")) { C->bary_enabled = value != 0; return EXTFEM_OK; }
-    if (key && !strcmp(key, "nonlinear_v2")) { C->nl_v2 = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "nonlinear_v2")) { C->nl_version = value != 0 ? 3 : 1; return EXTFEM_OK; }
+    if (key && !strcmp(key, "nonlinear_kernel")) { C->nl_version = std::min(std::max(value, 1), 3); return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_prefetch_ctas")) { C->tmpl_ahead = value < 0 ? 0 : value; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_pool_bytes")) { C->tmpl_pool = std::min(std::max(value, 4096), 200 * 1024); return EXTFEM_OK; }
@@ -1644,9 +1762,26 @@ int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc 
         }
         return worst;
     };
-    const bool v2 = C->nl_v2 && cv_entries(op.args, op.nargs) <= CVC_MAX && cv_entries(op.test, op.ntest) <= CVC_MAX && op.nin + op.nout <= 255;
+    const bool v2 = C->nl_version >= 2 && cv_entries(op.args, op.nargs) <= CVC_MAX && cv_entries(op.test, op.ntest) <= CVC_MAX && op.nin + op.nout <= 255;
+    NL3Tables T3;
+    bool v3 = false;
+    if (C->nl_version >= 3) if (int rc = build_nl3_tables(C, op, T3, &v3)) return rc;
     int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
         constexpr int DIM = decltype(dimc)::value;
+        if (v3) {
+            const size_t wd = nl3_warp_doubles(op.nq, op.nin, op.nout, op.NC, op.NR, T3.EC, T3.ER, T3.same, T3.phi_off[T3.nspaces]);
+            int nw = 8;
+            while (nw > 1 && (size_t)nw * wd * 8 + T3.tab_bytes > 100 * 1024) nw >>= 1;
+            const size_t smem = (size_t)nw * wd * 8 + T3.tab_bytes;
+            if (smem <= 200 * 1024) {
+                static bool attr_set3 = false;
+                if (!attr_set3) { cudaFuncSetAttribute(local_nonlinear_kernel3<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set3 = true; }
+                const int cpw = 4;   // cells per warp: amortises the table load of a block
+                local_nonlinear_kernel3<DIM><<<nblocks(op.ncells, nw * cpw), nw * 32, smem, C->stream>>>(op, T3, C->loc.as<double>(),
+                                                                                                      C->bloc.as<double>(), cpw);
+                return;
+            }
+        }
         if (v2) {
             const size_t per_cell = nl2_cell_bytes((int)sizeof(CellGeo<DIM>), op.nq, op.nin, op.nout, op.NR, op.NC);
             const int cpb = (int)std::max<size_t>(1, std::min<size_t>(8, (72 * 1024) / per_cell));

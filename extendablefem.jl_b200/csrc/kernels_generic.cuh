@@ -557,6 +557,7 @@ local_nonlinear_kernel(const __grid_constant__ OpDev op, double *__restrict__ lo
 //   A_loc     sum_q cvT . GJ    (<= 6 multiply-adds per point and entry), scaled by factor*|T| once per cell
 //             (nonlinear_operator.jl:396,419); rhs sum_q cvT . (J u - F) pre-scaled per point (:406)
 constexpr int CVC_MAX = 6;
+constexpr int NL2_MAXSP_ = 4;
 struct CVC {
     double v[CVC_MAX];
     unsigned char idx[CVC_MAX];
@@ -680,6 +681,157 @@ local_nonlinear_kernel2(const __grid_constant__ OpDev op, double *__restrict__ l
             }
         }
         bloc[(size_t)(c0 + s) * NR + k] = acc;
+    }
+}
+
+// ---- NonlinearOperator, warp per cell (v3) -------------------------------------------------------------
+// One warp owns one cell at a time; phases are separated by __syncwarp only (no block barriers), every phase runs over a
+// flattened item index decoded through small cell-independent lookup tables built on the host (no integer division):
+//   PHI  value / physical gradient of every scalar basis function at every point        items (point, function)
+//   B    operator vectors of the local dofs  B[q][x][j] = scale * PHI[...]               items (q, x, j)  -> gather table
+//   u,J  input_args, kernel value and Jacobian (w_q-scaled) per point                    lanes = points
+//   GJ   (w_q J_q) B_q[:, j]                                                             items (q, j, t)  -> packed table
+//   A    sum_q B_q^T GJ, scaled by factor*|T| once per cell; rhs from (J u - F)          items (j, k)     -> packed table
+// Rows and columns share one B table when test and args describe the same operators (the usual Newton setting).
+struct NL3Tables {
+    const unsigned char *tab;      // device table buffer (offsets below are bytes into it; 16-byte aligned pieces)
+    int tab_bytes;
+    int NC, NR, EC, ER, same;      // same != 0: rows use the column tables
+    int o_cn, o_cout, o_rn, o_rout;            // u8 [N], u8 [E][N]
+    int o_bgidx, o_bgsc, o_btidx, o_btsc;      // i32 / f64 [nq][E][N]: PHI index (-1: zero) and scale of B
+    int o_gj;                                  // u32 [nq*NC*nout]: q | j << 8 | t << 16
+    int o_ent;                                 // u16 [NR*NC]: j | k << 8
+    int nspaces, ns[NL2_MAXSP_];
+    const double *refvals[NL2_MAXSP_], *refgrads[NL2_MAXSP_];
+    int phi_off[NL2_MAXSP_ + 1];
+    int ncolblocks, blk_locoff[MAXARGS], blk_nd[MAXARGS];
+    const int *blk_celldofs[MAXARGS];
+    long long blk_soloff[MAXARGS];
+};
+
+__host__ __device__ inline size_t nl3_warp_doubles(int nq, int nin, int nout, int NC, int NR, int EC, int ER, int same, int phid)
+{
+    size_t d = (size_t)phid + (size_t)nq * EC * NC + (same ? 0 : (size_t)nq * ER * NR) + (size_t)nq * nin * nout + (size_t)nq * nout +
+               (size_t)nq * nin + (size_t)nq * NC * nout;
+    return (d + 1) & ~(size_t)1;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+local_nonlinear_kernel3(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tables T, double *__restrict__ loc,
+                        double *__restrict__ bloc, int cells_per_warp)
+{
+    extern __shared__ __align__(16) double smem_d[];
+    const int nin = op.nin, nout = op.nout, JS = nin * nout, nq = op.nq, NR = T.NR, NC = T.NC, NRC = NR * NC, EC = T.EC, ER = T.ER;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int phid = T.phi_off[T.nspaces];
+    const size_t wd = nl3_warp_doubles(nq, nin, nout, NC, NR, EC, ER, T.same, phid);
+    // block-shared tables behind the per-warp areas
+    unsigned char *tb = reinterpret_cast<unsigned char *>(smem_d + (size_t)nwarp * wd);
+    for (int i = threadIdx.x; i < T.tab_bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(tb)[i] = __ldg(reinterpret_cast<const uint4 *>(T.tab) + i);
+    __syncthreads();
+    const unsigned char *c_n = tb + T.o_cn, *c_out = tb + T.o_cout, *r_n = tb + T.o_rn, *r_out = tb + T.o_rout;
+    const int *bgidx = reinterpret_cast<const int *>(tb + T.o_bgidx), *btidx = reinterpret_cast<const int *>(tb + T.o_btidx);
+    const double *bgsc = reinterpret_cast<const double *>(tb + T.o_bgsc), *btsc = reinterpret_cast<const double *>(tb + T.o_btsc);
+    const unsigned *gjtab = reinterpret_cast<const unsigned *>(tb + T.o_gj);
+    const unsigned short *ent = reinterpret_cast<const unsigned short *>(tb + T.o_ent);
+    double *PHI = smem_d + (size_t)warp * wd;
+    double *BG = PHI + phid;                                       // [nq][EC][NC]
+    double *BT = T.same ? BG : BG + (size_t)nq * EC * NC;          // [nq][ER][NR]
+    double *Jq = (T.same ? BG : BT) + (T.same ? (size_t)nq * EC * NC : (size_t)nq * ER * NR);   // [nq][nout][nin]
+    double *rq = Jq + (size_t)nq * JS;                             // [nq][nout]
+    double *uq = rq + (size_t)nq * nout;                           // [nq][nin]
+    double *GJ = uq + (size_t)nq * nin;                            // [nq][NC][nout]
+    const long long cbase = ((long long)blockIdx.x * nwarp + warp) * cells_per_warp;
+    for (int ci = 0; ci < cells_per_warp; ++ci) {
+        const long long cell = cbase + ci;
+        if (cell >= op.ncells) break;
+        // geometry: every lane computes it redundantly (registers, no staging)
+        CellGeo<DIM> G;
+        load_geo<DIM>(op, cell, G);
+        __syncwarp();
+        // PHI
+        for (int sp = 0; sp < T.nspaces; ++sp) {
+            double *ph = PHI + T.phi_off[sp];
+            for (int e = lane; e < nq * T.ns[sp]; e += 32) {
+                double *o = ph + (size_t)e * (1 + DIM);
+                o[0] = __ldg(T.refvals[sp] + e);
+                const double *rg = T.refgrads[sp] + (size_t)e * DIM;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    double g = 0.0;
+#pragma unroll
+                    for (int r = 0; r < DIM; ++r) g += G.Ainv[r * DIM + d] * __ldg(rg + r);
+                    o[1 + d] = g;
+                }
+            }
+        }
+        __syncwarp();
+        // B tables
+        for (int i = lane; i < nq * EC * NC; i += 32) { const int p = bgidx[i]; BG[i] = p >= 0 ? bgsc[i] * PHI[p] : 0.0; }
+        if (!T.same)
+            for (int i = lane; i < nq * ER * NR; i += 32) { const int p = btidx[i]; BT[i] = p >= 0 ? btsc[i] * PHI[p] : 0.0; }
+        __syncwarp();
+        // input_args (lanes = points), kernel value and Jacobian
+        for (int q = lane; q < nq; q += 32) {
+            double *u = uq + q * nin;
+            for (int d = 0; d < nin; ++d) u[d] = 0.0;
+            for (int b = 0; b < T.ncolblocks; ++b) {
+                const int *dofs = T.blk_celldofs[b] + cell * T.blk_nd[b];
+                for (int jl = 0; jl < T.blk_nd[b]; ++jl) {
+                    const double sv = op.sol[T.blk_soloff[b] + dofs[jl]];
+                    const int j = T.blk_locoff[b] + jl, n = c_n[j];
+                    for (int x = 0; x < n; ++x) u[c_out[x * NC + j]] += sv * BG[((size_t)q * EC + x) * NC + j];
+                }
+            }
+            double ur[MAXOP], val[MAXOP];
+            for (int d = 0; d < nin; ++d) ur[d] = u[d];
+            double *J = Jq + (size_t)q * JS;
+            nl_apply(op.kernel_id, DIM, ur, op.params, val, J, nin, nout);
+            const double w = op.qw[q], sc = op.factor * w * G.vol;
+            for (int k = 0; k < nout; ++k) {
+                double sum = 0.0;
+                for (int d = 0; d < nin; ++d) { sum += J[k * nin + d] * ur[d]; J[k * nin + d] *= w; }
+                rq[q * nout + k] = (sum - val[k]) * sc;
+            }
+        }
+        __syncwarp();
+        // GJ[q][j][t]
+        for (int i = lane; i < nq * NC * nout; i += 32) {
+            const unsigned pk = gjtab[i];
+            const int q = pk & 0xff, j = (pk >> 8) & 0xff, t = pk >> 16, n = c_n[j];
+            const double *Jr = Jq + (size_t)q * JS + t * nin;
+            const double *bg = BG + (size_t)q * EC * NC + j;
+            double a = 0.0;
+            for (int x = 0; x < n; ++x) a += Jr[c_out[x * NC + j]] * bg[(size_t)x * NC];
+            GJ[i] = a;
+        }
+        __syncwarp();
+        // local matrix (lanes = consecutive entries = consecutive rows of one column) and vector
+        const double fv = G.visited ? op.factor * G.vol : 0.0;
+        double *out = loc + (size_t)cell * NRC;
+        for (int e = lane; e < NRC; e += 32) {
+            const int j = ent[e] & 0xff, k = ent[e] >> 8, n = r_n[k];
+            double acc = 0.0;
+            for (int x = 0; x < n; ++x) {
+                const double *b = BT + (size_t)x * NR + k;
+                const double *g = GJ + (size_t)j * nout + r_out[x * NR + k];
+                for (int q = 0; q < nq; ++q) acc += b[(size_t)q * ER * NR] * g[(size_t)q * NC * nout];
+            }
+            out[e] = acc * fv;
+        }
+        double *bout = bloc + (size_t)cell * NR;
+        for (int k = lane; k < NR; k += 32) {
+            const int n = r_n[k];
+            double acc = 0.0;
+            for (int x = 0; x < n; ++x) {
+                const double *b = BT + (size_t)x * NR + k;
+                const double *f = rq + r_out[x * NR + k];
+                for (int q = 0; q < nq; ++q) acc += f[q * nout] * b[(size_t)q * ER * NR];
+            }
+            bout[k] = G.visited ? acc : 0.0;
+        }
+        __syncwarp();
     }
 }
 

@@ -283,15 +283,19 @@ def test_nonlinear_local_kernel_versions_agree(pkg, ora, engine, case):
         sol = u.entries
         args = [(0, GRAD)]
         desc = engine.make_opdesc(args, args=args, kernel_id=pkg.lib.kernel_id("neohooke3d"), params=[3.8, 5.7], regions=(1,))
-    a2 = np.empty(S.rowval.size); b2 = np.empty(S.N); a1 = np.empty(S.rowval.size); b1 = np.empty(S.N)
-    engine.assemble_nonlinear(S.pat, desc, sol, nzval_out=a2, b_out=b2)
-    engine.set_option("nonlinear_v2", 0)
+    res = {}
     try:
-        engine.assemble_nonlinear(S.pat, desc, sol, nzval_out=a1, b_out=b1)
+        for ver in (1, 2, 3):     # entry-wise | staged per block | warp per cell (default)
+            engine.set_option("nonlinear_kernel", ver)
+            a = np.empty(S.rowval.size); b = np.empty(S.N)
+            engine.assemble_nonlinear(S.pat, desc, sol, nzval_out=a, b_out=b)
+            res[ver] = (a, b)
     finally:
-        engine.set_option("nonlinear_v2", 1)
-    check_values(a2, a1, rtol=1e-13, what="jacobian v2 vs v1")
-    check_values(b2, b1, rtol=1e-13, scale=max(np.abs(b1).max(), np.abs(a1).max() * np.abs(sol).max()), what="rhs v2 vs v1")
+        engine.set_option("nonlinear_kernel", 3)
+    a1, b1 = res[1]
+    for ver in (2, 3):
+        check_values(res[ver][0], a1, rtol=1e-13, what=f"jacobian v{ver} vs v1")
+        check_values(res[ver][1], b1, rtol=1e-13, scale=max(np.abs(b1).max(), np.abs(a1).max() * np.abs(sol).max()), what=f"rhs v{ver} vs v1")
 
 
 def test_nonlinear_equals_bilinear_for_linear_kernel(pkg, ora, engine):
