@@ -1191,17 +1191,47 @@ static int build_nl3_tables(Ctx *ctx, const OpDev &op, NL3Tables &T, bool *ok)
     pack(cols, op.NC, T.EC, T.o_cn, T.o_cout, T.o_bgidx, T.o_bgsc);
     if (same) { T.ER = T.EC; T.o_rn = T.o_cn; T.o_rout = T.o_cout; T.o_btidx = T.o_bgidx; T.o_btsc = T.o_bgsc; }
     else pack(rows, op.NR, T.ER, T.o_rn, T.o_rout, T.o_btidx, T.o_btsc);
-    T.o_gj = reserve((size_t)op.nq * op.NC * op.nout * 4);
+    if ((size_t)op.nq * op.nin * op.nout >= 65536 || (size_t)op.nq * T.EC * op.NC >= 65536 || (size_t)op.nq * T.ER * op.NR >= 65536 ||
+        (size_t)op.nq * op.NC * op.nout >= 65536)
+        return 0;   // 16-bit offsets
+    const std::vector<NL3Dof> &rws = same ? cols : rows;
+    T.o_gjj = reserve((size_t)op.nq * op.NC * op.nout * T.EC * 2);
+    T.o_gjb = reserve((size_t)op.nq * op.NC * op.nout * T.EC * 2);
     {
-        unsigned *gj = reinterpret_cast<unsigned *>(host.data() + T.o_gj);
         size_t i = 0;
         for (int q = 0; q < op.nq; ++q)
             for (int j = 0; j < op.NC; ++j)
-                for (int t = 0; t < op.nout; ++t) gj[i++] = (unsigned)q | ((unsigned)j << 8) | ((unsigned)t << 16);
+                for (int t = 0; t < op.nout; ++t, ++i)
+                    for (int x = 0; x < T.EC; ++x) {
+                        const bool live = x < cols[j].n;
+                        reinterpret_cast<unsigned short *>(host.data() + T.o_gjj)[i * T.EC + x] =
+                            (unsigned short)(q * op.nin * op.nout + t * op.nin + (live ? cols[j].out[x] : 0));
+                        reinterpret_cast<unsigned short *>(host.data() + T.o_gjb)[i * T.EC + x] = (unsigned short)((q * T.EC + x) * op.NC + j);
+                    }
     }
-    T.o_ent = reserve((size_t)op.NR * op.NC * 2);
+    T.o_enb = reserve((size_t)op.NR * op.NC * T.ER * 2);
+    T.o_eng = reserve((size_t)op.NR * op.NC * T.ER * 2);
     for (int j = 0; j < op.NC; ++j)
-        for (int k = 0; k < op.NR; ++k) reinterpret_cast<unsigned short *>(host.data() + T.o_ent)[(size_t)j * op.NR + k] = (unsigned short)(j | (k << 8));
+        for (int k = 0; k < op.NR; ++k)
+            for (int x = 0; x < T.ER; ++x) {
+                const size_t i = ((size_t)j * op.NR + k) * T.ER + x;
+                const bool live = x < rws[k].n;
+                reinterpret_cast<unsigned short *>(host.data() + T.o_enb)[i] = (unsigned short)(x * op.NR + k);
+                reinterpret_cast<unsigned short *>(host.data() + T.o_eng)[i] = (unsigned short)(j * op.nout + (live ? rws[k].out[x] : 0));
+            }
+    {
+        std::vector<unsigned short> uptr(op.nin + 1, 0), ulist;
+        for (int o = 0; o < op.nin; ++o) {
+            for (int j = 0; j < op.NC; ++j)
+                for (int x = 0; x < cols[j].n; ++x)
+                    if (cols[j].out[x] == o) ulist.push_back((unsigned short)(j | (x << 8)));
+            uptr[o + 1] = (unsigned short)ulist.size();
+        }
+        T.o_uptr = reserve(uptr.size() * 2);
+        memcpy(host.data() + T.o_uptr, uptr.data(), uptr.size() * 2);
+        T.o_ulist = reserve(std::max<size_t>(ulist.size(), 1) * 2);
+        if (!ulist.empty()) memcpy(host.data() + T.o_ulist, ulist.data(), ulist.size() * 2);
+    }
     reserve(0);
     host.resize((host.size() + 15) / 16 * 16, 0);
     T.tab_bytes = (int)host.size();

@@ -699,8 +699,10 @@ struct NL3Tables {
     int NC, NR, EC, ER, same;      // same != 0: rows use the column tables
     int o_cn, o_cout, o_rn, o_rout;            // u8 [N], u8 [E][N]
     int o_bgidx, o_bgsc, o_btidx, o_btsc;      // i32 / f64 [nq][E][N]: PHI index (-1: zero) and scale of B
-    int o_gj;                                  // u32 [nq*NC*nout]: q | j << 8 | t << 16
-    int o_ent;                                 // u16 [NR*NC]: j | k << 8
+    int o_gjj, o_gjb;                          // u16 [nq*NC*nout][EC]: offsets into J (q*JS + t*nin + out_x) and into B
+    int o_enb, o_eng;                          // u16 [NR*NC][ER]: offsets of BT[0][x][k] and of GJ[0][j][out_x(k)]
+    int o_uptr, o_ulist;                       // input_args: per result index o the (j | x << 8) pairs with out == o
+    int o_ucol;                                // i32 [NC]: offset of the column dof in the cell's solution gather (block, dof)
     int nspaces, ns[NL2_MAXSP_];
     const double *refvals[NL2_MAXSP_], *refgrads[NL2_MAXSP_];
     int phi_off[NL2_MAXSP_ + 1];
@@ -712,7 +714,7 @@ struct NL3Tables {
 __host__ __device__ inline size_t nl3_warp_doubles(int nq, int nin, int nout, int NC, int NR, int EC, int ER, int same, int phid)
 {
     size_t d = (size_t)phid + (size_t)nq * EC * NC + (same ? 0 : (size_t)nq * ER * NR) + (size_t)nq * nin * nout + (size_t)nq * nout +
-               (size_t)nq * nin + (size_t)nq * NC * nout;
+               (size_t)nq * nin + (size_t)nq * NC * nout + (size_t)NC;
     return (d + 1) & ~(size_t)1;
 }
 
@@ -733,8 +735,9 @@ local_nonlinear_kernel3(const __grid_constant__ OpDev op, const __grid_constant_
     const unsigned char *c_n = tb + T.o_cn, *c_out = tb + T.o_cout, *r_n = tb + T.o_rn, *r_out = tb + T.o_rout;
     const int *bgidx = reinterpret_cast<const int *>(tb + T.o_bgidx), *btidx = reinterpret_cast<const int *>(tb + T.o_btidx);
     const double *bgsc = reinterpret_cast<const double *>(tb + T.o_bgsc), *btsc = reinterpret_cast<const double *>(tb + T.o_btsc);
-    const unsigned *gjtab = reinterpret_cast<const unsigned *>(tb + T.o_gj);
-    const unsigned short *ent = reinterpret_cast<const unsigned short *>(tb + T.o_ent);
+    const unsigned short *gjj = reinterpret_cast<const unsigned short *>(tb + T.o_gjj), *gjb = reinterpret_cast<const unsigned short *>(tb + T.o_gjb);
+    const unsigned short *enb = reinterpret_cast<const unsigned short *>(tb + T.o_enb), *eng = reinterpret_cast<const unsigned short *>(tb + T.o_eng);
+    const unsigned short *uptr = reinterpret_cast<const unsigned short *>(tb + T.o_uptr), *ulist = reinterpret_cast<const unsigned short *>(tb + T.o_ulist);
     double *PHI = smem_d + (size_t)warp * wd;
     double *BG = PHI + phid;                                       // [nq][EC][NC]
     double *BT = T.same ? BG : BG + (size_t)nq * EC * NC;          // [nq][ER][NR]
@@ -742,6 +745,7 @@ local_nonlinear_kernel3(const __grid_constant__ OpDev op, const __grid_constant_
     double *rq = Jq + (size_t)nq * JS;                             // [nq][nout]
     double *uq = rq + (size_t)nq * nout;                           // [nq][nin]
     double *GJ = uq + (size_t)nq * nin;                            // [nq][NC][nout]
+    double *solc = GJ + (size_t)nq * NC * nout;                    // [NC] solution values of the cell's column dofs
     const long long cbase = ((long long)blockIdx.x * nwarp + warp) * cells_per_warp;
     for (int ci = 0; ci < cells_per_warp; ++ci) {
         const long long cell = cbase + ci;
@@ -772,20 +776,28 @@ local_nonlinear_kernel3(const __grid_constant__ OpDev op, const __grid_constant_
         if (!T.same)
             for (int i = lane; i < nq * ER * NR; i += 32) { const int p = btidx[i]; BT[i] = p >= 0 ? btsc[i] * PHI[p] : 0.0; }
         __syncwarp();
-        // input_args (lanes = points), kernel value and Jacobian
-        for (int q = lane; q < nq; q += 32) {
-            double *u = uq + q * nin;
-            for (int d = 0; d < nin; ++d) u[d] = 0.0;
-            for (int b = 0; b < T.ncolblocks; ++b) {
-                const int *dofs = T.blk_celldofs[b] + cell * T.blk_nd[b];
-                for (int jl = 0; jl < T.blk_nd[b]; ++jl) {
-                    const double sv = op.sol[T.blk_soloff[b] + dofs[jl]];
-                    const int j = T.blk_locoff[b] + jl, n = c_n[j];
-                    for (int x = 0; x < n; ++x) u[c_out[x * NC + j]] += sv * BG[((size_t)q * EC + x) * NC + j];
-                }
+        // solution values of the cell's column dofs
+        for (int b = 0; b < T.ncolblocks; ++b) {
+            const int *dofs = T.blk_celldofs[b] + cell * T.blk_nd[b];
+            for (int jl = lane; jl < T.blk_nd[b]; jl += 32) solc[T.blk_locoff[b] + jl] = op.sol[T.blk_soloff[b] + dofs[jl]];
+        }
+        __syncwarp();
+        // input_args: items (point, result index) sum over the (dof, entry) pairs that feed the index
+        for (int i = lane; i < nq * nin; i += 32) {
+            const int q = i / nin, o = i - q * nin;
+            const double *bg = BG + (size_t)q * EC * NC;
+            double a = 0.0;
+            for (int p = uptr[o]; p < uptr[o + 1]; ++p) {
+                const int j = ulist[p] & 0xff, x = ulist[p] >> 8;
+                a += solc[j] * bg[x * NC + j];
             }
+            uq[i] = a;
+        }
+        __syncwarp();
+        // kernel value and Jacobian (lanes = points)
+        for (int q = lane; q < nq; q += 32) {
             double ur[MAXOP], val[MAXOP];
-            for (int d = 0; d < nin; ++d) ur[d] = u[d];
+            for (int d = 0; d < nin; ++d) ur[d] = uq[q * nin + d];
             double *J = Jq + (size_t)q * JS;
             nl_apply(op.kernel_id, DIM, ur, op.params, val, J, nin, nout);
             const double w = op.qw[q], sc = op.factor * w * G.vol;
@@ -796,27 +808,25 @@ local_nonlinear_kernel3(const __grid_constant__ OpDev op, const __grid_constant_
             }
         }
         __syncwarp();
-        // GJ[q][j][t]
+        // GJ[q][j][t]: EC multiply-adds per item through direct offset tables (padding entries hit zeros of B)
         for (int i = lane; i < nq * NC * nout; i += 32) {
-            const unsigned pk = gjtab[i];
-            const int q = pk & 0xff, j = (pk >> 8) & 0xff, t = pk >> 16, n = c_n[j];
-            const double *Jr = Jq + (size_t)q * JS + t * nin;
-            const double *bg = BG + (size_t)q * EC * NC + j;
+            const unsigned short *oj = gjj + (size_t)i * EC, *ob = gjb + (size_t)i * EC;
             double a = 0.0;
-            for (int x = 0; x < n; ++x) a += Jr[c_out[x * NC + j]] * bg[(size_t)x * NC];
+            for (int x = 0; x < EC; ++x) a += Jq[oj[x]] * BG[ob[x]];
             GJ[i] = a;
         }
         __syncwarp();
         // local matrix (lanes = consecutive entries = consecutive rows of one column) and vector
         const double fv = G.visited ? op.factor * G.vol : 0.0;
         double *out = loc + (size_t)cell * NRC;
+        const int sb = ER * NR, sg = NC * nout;
         for (int e = lane; e < NRC; e += 32) {
-            const int j = ent[e] & 0xff, k = ent[e] >> 8, n = r_n[k];
+            const unsigned short *ob = enb + (size_t)e * ER, *og = eng + (size_t)e * ER;
             double acc = 0.0;
-            for (int x = 0; x < n; ++x) {
-                const double *b = BT + (size_t)x * NR + k;
-                const double *g = GJ + (size_t)j * nout + r_out[x * NR + k];
-                for (int q = 0; q < nq; ++q) acc += b[(size_t)q * ER * NR] * g[(size_t)q * NC * nout];
+            for (int x = 0; x < ER; ++x) {
+                const double *b = BT + ob[x];
+                const double *g = GJ + og[x];
+                for (int q = 0; q < nq; ++q) acc += b[(size_t)q * sb] * g[(size_t)q * sg];
             }
             out[e] = acc * fv;
         }
