@@ -1,24 +1,8 @@
-# INTEGRATION — binding `libextfem_cuda.so` into ExtendableFEM.jl
-
-The reference has no plugin/FFI interface; its hot path sits behind Julia multiple dispatch on
-`AbstractOperator` (`src/operators.jl:6-41`). The narrowest seam is the closure `O.assembler` built
-by `build_assembler!` and invoked by `assemble!` with raw arrays:
-
-| Operator | `build_assembler!` | closure call the library replaces |
-|---|---|---|
-| `BilinearOperator` | `src/common_operators/bilinear_operator.jl:659` | `O.assembler(A.entries, b.entries[, sol blocks])` `:1028,1031` |
-| `LinearOperator` | `src/common_operators/linear_operator.jl:482` / `:241` | `O.assembler(b.entries[, sol blocks])` `:710,713` |
-| `NonlinearOperator` | `src/common_operators/nonlinear_operator.jl:129` | `O.assembler(A.entries, b.entries, sol blocks; time)` `:491` |
-| zeroing / penalties / residual | `src/solvers.jl:124-195`, `:38-43` | `accumulate` flag, `extfem_apply_penalties`, `extfem_residual` |
-
-Entry points are declared in `include/extfem_cuda.h` (each one cites the reference lines it stands
-for). All data pointers are plain host *or* device pointers; sizes are explicit; there are no torch
-or Julia types in any signature; every function returns `0` or a negative `EXTFEM_ERR_*` and
-`extfem_last_error(ctx)` returns the message.
-
-## Julia side (`extendablefem.jl_b200/julia/ExtFEMCuda.jl`; a maintainer adds it as `ext/ExtendableFEMCudaExt.jl`; untested here — Julia is not in the build image)
-
-```julia
+# ExtFEMCuda.jl -- ccall glue between ExtendableFEM.jl and libextfem_cuda.so (include/extfem_cuda.h).
+#
+# UNTESTED in this repository: Julia is not part of the build image.  It is the file a maintainer adds as
+# ext/ExtendableFEMCudaExt.jl; INTEGRATION.md explains every call and cites the reference lines it replaces
+# (O.assembler closures built in src/common_operators/*_operator.jl: build_assembler!).
 module ExtFEMCuda
 using ExtendableFEM, ExtendableFEMBase, ExtendableGrids, SparseArrays
 const lib = "libextfem_cuda"            # extendablefem.jl_b200/csrc/libextfem_cuda.so on LD_LIBRARY_PATH
@@ -101,48 +85,3 @@ end
 # (sol = sol.entries, b_out = b.entries); HomogeneousData.apply_penalties! -> extfem_apply_penalties;
 # compute_nonlinear_residual! (solvers.jl:38-43) -> extfem_residual.
 end
-```
-
-`OpDesc` is filled from the operator's kwargs table (`bilinear_operator.jl:56-73`): `test_op/ansatz_op`
-from `O.ops_test/ops_ansatz` (`Identity→0, Gradient→1, Divergence→2, SymmetricGradient{offdiag}→3`),
-`*_block` from `get_unknown_id(SC, u) - 1`, `factor`, `quadorder` (`-1` for `"auto"`), `bonus_quadorder`,
-`regions`, `transposed_copy`, `lump`, `params`, and `qweights/qpoints` from
-`QuadratureRule{Tv,EG}(quadorder)` so that the engine integrates with ExtendableFEMBase's own rule.
-`O.assembler = gpu_assembler(...)` is set in a `build_assembler!` method specialised on a
-`GPUBackend` tag stored in `O.parameters[:backend]`; `solve`, `ProblemDescription` and
-`assign_operator!` are untouched.
-
-## Python side (what the tests in this repo use)
-
-`extendablefem.jl_b200/host/lib.py` is the ctypes twin of the stubs above (`Engine.mesh_set`,
-`space_set`, `pattern_build`, `assemble_*`, …); `host/grids.py` and `host/fespace.py` mirror
-`simplexgrid`, `uniform_refine`, `FESpace{H1Pk}` so the parity tests read like the reference's tests.
-
-## Multi-GPU
-One process (Julia: one `Distributed` worker or MPI rank) per GPU; `include/extfem_cuda.h` section "multi-GPU":
-
-```julia
-# rank 0 creates the NCCL id, the host broadcasts the 128 bytes (MPI.Bcast! / Distributed), every rank joins
-id = Vector{UInt8}(undef, 128)
-rank == 0 && check(C_NULL, ccall((:extfem_dist_unique_id, lib), Cint, (Ptr{UInt8},), id))
-MPI.Bcast!(id, 0, comm)
-check(ctx.ptr, ccall((:extfem_dist_init, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx.ptr, rank, world, id))
-# local grid = this rank's cell range (ExtendableGrids.subgrid / partition), local FESpace on it; interface rows per
-# neighbour in ascending global dof id, ownership = lowest rank (host/dist.py: Shard, build_interface_plan)
-check(ctx.ptr, ccall((:extfem_dist_set_interfaces, lib), Cint,
-      (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}, Ptr{UInt8}), ctx.ptr, pattern, length(neigh), neigh, ptr, rows, owned))
-# after the local assemble! calls:
-check(ctx.ptr, ccall((:extfem_dist_sum_rhs, lib), Cint, (Ptr{Cvoid}, Cint), ctx.ptr, pattern))      # b consistent
-check(ctx.ptr, ccall((:extfem_dist_cg, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Float64, Cint, Ptr{Cint}, Ptr{Float64}),
-      ctx.ptr, pattern, C_NULL, x, 1e-10, 10_000, iters, relres))
-```
-
-The Python twin is `Engine.dist_init / dist_set_interfaces / dist_sum_rhs / dist_spmv / dist_cg`
-(`host/lib.py`) with `host/dist.py` for the partition and interface plan; `tests/dist_worker.py` is a complete
-example (2 ranks, NCCL). Design and exchanged volumes: DESIGN.md §5.
-
-## Diagnostics
-`extfem_plan_stats` (period of the geometry order, templates, template warps, columns on the record kernel, …),
-`extfem_last_timings` (device ms of the cell and gather phases of the last assemble call), `extfem_launch_count`,
-`extfem_set_option` (`fastpath`, `fastpath_closed_form`, `fastpath_templates`, `template_min_cols`,
-`template_pool_bytes`, `template_prefetch_ctas`, `template_constant_memory`, `template_permute_mesh`, `nonlinear_kernel`).
