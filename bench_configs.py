@@ -117,7 +117,13 @@ def config5(pkg, n, order, iters):
     plan = slab_interfaces(pkg, FES, rank, world) if world > 1 else pkg.InterfacePlan(0, 1, np.zeros(0, np.int32), np.zeros(1, np.int64),
                                                                                   np.zeros(0, np.int64), np.ones(FES.ndofs, np.uint8))
     eng.dist_set_interfaces(pat, plan)
-    eng.assemble_bilinear(pat, eng.make_opdesc([(0, 1)], [(0, 1)]))
+    lap = eng.make_opdesc([(0, 1)], [(0, 1)])
+    eng.assemble_bilinear(pat, lap)
+    asm_ms = []
+    for _ in range(3):
+        eng.event_record(0); eng.assemble_bilinear(pat, lap); eng.event_record(1)
+        asm_ms.append(eng.event_elapsed_ms(0, 1))
+    asm_phase = eng.last_timings()
     eng.assemble_linear(pat, eng.make_opdesc([(0, 0)], kernel_id=pkg.lib.kernel_id("sincos301"), params=[1.0]))
     eng.dist_sum_rhs(pat)
     # homogeneous Dirichlet data on the outer boundary of the stacked domain (owner applies the penalty)
@@ -145,7 +151,9 @@ def config5(pkg, n, order, iters):
     if rank == 0:
         per_it = dt / max(1, it)
         out = {"config": 5, "workload": f"3D H1P{order} Poisson + Jacobi-CG, slab n={n} per GPU ({grid.ncells} tets, {nrows} dofs, {nnz} nnz per GPU)",
-               "n_gpus": world, "cg_iterations": it, "relres": rr, "ms_per_iteration": per_it * 1e3,
+               "n_gpus": world, "stiffness_assembly_ms": float(np.median(asm_ms)), "stiffness_phase_ms": asm_phase[:2],
+               "stiffness_cells_per_s_per_gpu": grid.ncells / float(np.median(asm_ms)) * 1e3, "plan": eng.plan_stats(pat, 0),
+               "cg_iterations": it, "relres": rr, "ms_per_iteration": per_it * 1e3,
                "spmv_algorithmic_GBs_per_gpu": (12.0 * nnz + 16.0 * nrows) / per_it / 1e9,
                "note": "one SpMV + interface-row exchange (ncclSend/Recv) + 3 dot products (ncclAllReduce) + 2 vector updates per iteration; "
                        "measured as the difference of two runs of different length (host copies of x excluded)"}
