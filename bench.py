@@ -330,9 +330,11 @@ def run_reference(args):
 
 
 def main():
-    # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION; rank 0 must print exactly one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 must print exactly ONE JSON line on stdout: route everything libraries write to file descriptor 1 (NCCL prints
+    # its version banner there) to stderr for the duration of the run and restore stdout for the result line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -344,8 +346,10 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if out is not None:
-        sys.stdout.flush()
         print(json.dumps(out), flush=True)
 
 
