@@ -114,6 +114,7 @@ struct Ctx {
     bool tmpl_enabled = true;   // option "fastpath_templates": 0 keeps every column on the record kernel
     int tmpl_ahead = 1024;      // option "template_prefetch_ctas": CTAs ahead whose start-up data is prefetched into L2
     int tmpl_pool = TP_POOL_BYTES; // option "template_pool_bytes": shared-memory pool of one template CTA
+    bool tmpl_planemask = true; // option "template_plane_mask": rounds load only the geometry values their local column reads
     bool tmpl_const = true;     // option "template_constant_memory": template rounds in constant memory when they fit
     const void *const_tmpl_owner = nullptr;
     bool tmpl_permute_mesh = true; // option "template_permute_mesh": cell kernels read mesh copies in the transposed order
@@ -926,6 +927,12 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
             EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_tmpl, T.tmpl.p, (size_t)T.nrounds * TP_TW * 4, 0, cudaMemcpyDeviceToDevice, ctx->stream));
             ctx->const_tmpl_owner = &T;
         }
+        {
+            unsigned pm[16];
+            for (int kl = 0; kl < 16; ++kl) pm[kl] = ctx->tmpl_planemask ? EV::plane_mask(kl < EV::NS ? kl : 0) : (1u << EV::NG) - 1u;
+            EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_planemask, pm, sizeof(pm), 0, cudaMemcpyHostToDevice, ctx->stream));
+            EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // pm lives on the stack
+        }
         int rc;
         if (ct) rc = first ? launch_template<EV, true, true>(ctx, P, T, b, accumulate) : launch_template<EV, false, true>(ctx, P, T, b, accumulate);
         else rc = first ? launch_template<EV, true, false>(ctx, P, T, b, accumulate) : launch_template<EV, false, false>(ctx, P, T, b, accumulate);
@@ -1424,6 +1431,7 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_prefetch_ctas")) { C->tmpl_ahead = value < 0 ? 0 : value; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_pool_bytes")) { C->tmpl_pool = std::min(std::max(value, 4096), 200 * 1024); return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_plane_mask")) { C->tmpl_planemask = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_constant_memory")) { C->tmpl_const = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_permute_mesh")) { C->tmpl_permute_mesh = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_min_cols")) { C->tmpl_mincols = value < 1 ? 1 : value; return EXTFEM_OK; }

@@ -305,6 +305,8 @@ struct EvalTable {
     // slot of local row t for a column with local index kl, -1: none.  Any element: the column dof itself.
     static constexpr int NCOMMON = 1;
     __host__ __device__ static constexpr int common_slot(int kl, int t) { return t == kl ? 0 : -1; }
+    // geometry values (bit g) that local column kl reads: all of them for the table evaluator
+    __host__ __device__ static constexpr unsigned plane_mask(int) { return (1u << NG) - 1u; }
     template <int KL, int T0, int T1>
     __device__ __forceinline__ static void column(const double (&G)[NG], double (&cur)[NS])
     {
@@ -321,6 +323,17 @@ struct EvalTable {
 template <int DIM, int ORDER>
 struct EvalBary {
     static constexpr int NV = DIM + 1, NS = ORDER == 1 ? DIM + 1 : (DIM + 1) * (DIM + 2) / 2, NG = DIM * (DIM + 1) / 2;
+    // geometry values (bit g = pair index of D_ab) that local column kl reads: the closed form only touches rows of the Gram
+    // matrix that belong to the column dof's vertices (the vertex itself, or the two end points of its edge)
+    __host__ __device__ static constexpr unsigned plane_mask(int kl)
+    {
+        unsigned m = 0;
+        const int v0 = kl < NV ? kl : fp_edge_a<DIM>(kl - NV), v1 = kl < NV ? kl : fp_edge_b<DIM>(kl - NV);
+        for (int a = 0; a <= DIM; ++a)
+            for (int b = a + 1; b <= DIM; ++b)
+                if (a == v0 || b == v0 || a == v1 || b == v1) m |= 1u << fp_pair_index<DIM>(a, b);
+        return m;
+    }
     // P2: every cell around an edge dof also holds the edge's two end points: slots 1 / 2 (local edge vertices a / b)
     static constexpr int NCOMMON = ORDER == 2 ? 3 : 1;
     __host__ __device__ static constexpr int common_slot(int kl, int t)
