@@ -124,6 +124,8 @@ struct Ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t uev[16] = {};
     double last_ms[3] = {0, 0, 0};
+    bool timing_pending = false;
+    const void *planemask_owner = nullptr;
 };
 
 static std::string g_last_error;
@@ -266,6 +268,7 @@ struct Prepared {
     std::vector<int> testblocks, colblocks; // unique blocks (ascending)
     std::vector<int> testlocoff, collocoff;  // operator-local offsets of these blocks
     int quadorder = 0;
+    QuadRule Q;                              // host copy of the operator's quadrature rule
 };
 
 enum OpKind { KIND_BILINEAR = 0, KIND_LINEAR = 1, KIND_NONLINEAR = 2 };
@@ -363,6 +366,7 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
         op.qw = dq->w.as<double>(); op.qx = dq->x.as<double>();
     }
     op.nq = Q.nq;
+    R.Q = Q;
 
     // --- unique blocks and operator-local layout
     auto uniq = [](std::vector<int> v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); return v; };
@@ -520,9 +524,21 @@ static int gather_vector(Ctx *ctx, Pattern &P, const Prepared &R, int accumulate
     return 0;
 }
 
-static int finish_timing(Ctx *ctx)
+// Results that stay device-resident do not make the call wait for the GPU (the host runs ahead and prepares the next
+// operator); copies into caller memory do.  extfem_last_timings / extfem_synchronize wait.
+static int collect_timing(Ctx *ctx);
+static int finish_timing(Ctx *ctx, bool wait)
 {
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->timing_pending = true;
+    if (!wait) return 0;
+    return collect_timing(ctx);
+}
+
+static int collect_timing(Ctx *ctx)
+{
+    if (!ctx->timing_pending) return 0;
+    ctx->timing_pending = false;
     EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     float a = 0, b = 0, c = 0;
     cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
@@ -928,10 +944,15 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
             ctx->const_tmpl_owner = &T;
         }
         {
-            unsigned pm[16];
-            for (int kl = 0; kl < 16; ++kl) pm[kl] = ctx->tmpl_planemask ? EV::plane_mask(kl < EV::NS ? kl : 0) : (1u << EV::NG) - 1u;
-            EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_planemask, pm, sizeof(pm), 0, cudaMemcpyHostToDevice, ctx->stream));
-            EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // pm lives on the stack
+            static const char ev_tag = 0;   // one per evaluator instantiation
+            const void *owner = ctx->tmpl_planemask ? (const void *)&ev_tag : (const void *)ctx;
+            if (ctx->planemask_owner != owner) {
+                unsigned pm[16];
+                for (int kl = 0; kl < 16; ++kl) pm[kl] = ctx->tmpl_planemask ? EV::plane_mask(kl < EV::NS ? kl : 0) : (1u << EV::NG) - 1u;
+                EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_planemask, pm, sizeof(pm), 0, cudaMemcpyHostToDevice, ctx->stream));
+                EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // pm lives on the stack
+                ctx->planemask_owner = owner;
+            }
         }
         int rc;
         if (ct) rc = first ? launch_template<EV, true, true>(ctx, P, T, b, accumulate) : launch_template<EV, false, true>(ctx, P, T, b, accumulate);
@@ -1079,12 +1100,7 @@ static int try_fast_bilinear(Ctx *ctx, Pattern &P, const Prepared &R, const extf
             EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(P.nzval.as<double>() + n0, 0, (size_t)(n1 - n0) * 8, ctx->stream));
         }
     }
-    QuadRule Q;
-    Q.dim = dim; Q.nq = op.nq;
-    Q.w.resize(op.nq); Q.x.resize((size_t)op.nq * dim);
-    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.w.data(), op.qw, op.nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.x.data(), op.qx, (size_t)op.nq * dim * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const QuadRule &Q = R.Q;   // host copy kept by prepare(): no device round trip
     std::vector<double> T = fast_tables(Q, S.order, dim, form);
     int rc = -1;
     // closed-form barycentric evaluators (Laplace, P1/P2, 2D/3D), verified against the tables
@@ -1278,12 +1294,7 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
     if (int rc = build_template_plan(ctx, P, b, ns)) return rc;
     TemplatePlan &T = *P.tplans[b];
     // reference basis values at the operator's quadrature points
-    QuadRule Q;
-    Q.dim = dim; Q.nq = op.nq;
-    Q.w.resize(op.nq); Q.x.resize((size_t)op.nq * dim);
-    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.w.data(), op.qw, op.nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(Q.x.data(), op.qx, (size_t)op.nq * dim * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const QuadRule &Q = R.Q;   // host copy kept by prepare(): no device round trip
     std::vector<double> v, g, phi((size_t)10 * TP_NQMAX, 0.0);
     ref_basis(S.order, dim, Q, v, g);
     for (int q = 0; q < op.nq; ++q)
@@ -1443,6 +1454,7 @@ int64_t extfem_launch_count(extfem_ctx *ctx) { return ctx ? reinterpret_cast<Ctx
 int extfem_last_timings(extfem_ctx *ctx, double *ms3)
 {
     CTX_GUARD(ctx);
+    if (int rc = collect_timing(C)) return rc;
     for (int i = 0; i < 3; ++i) ms3[i] = C->last_ms[i];
     return EXTFEM_OK;
 }
@@ -1730,7 +1742,7 @@ int extfem_assemble_bilinear(extfem_ctx *ctx, int pattern, const extfem_opdesc *
         EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[2], C->stream));
     }
     if (nzval_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(nzval_out, P.nzval.p, (size_t)P.nnz * 8, cudaMemcpyDefault, C->stream));
-    return finish_timing(C);
+    return finish_timing(C, nzval_out != nullptr);
 }
 
 int extfem_assemble_linear(extfem_ctx *ctx, int pattern, const extfem_opdesc *d, const double *sol, int accumulate, double *b_out)
@@ -1759,7 +1771,7 @@ int extfem_assemble_linear(extfem_ctx *ctx, int pattern, const extfem_opdesc *d,
         EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[2], C->stream));
     }
     if (b_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b_out, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
-    return finish_timing(C);
+    return finish_timing(C, b_out != nullptr);
 }
 
 /* statistics of the fast-path plans of column block `block` (built on first use):
@@ -1843,7 +1855,7 @@ int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc 
     EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[2], C->stream));
     if (nzval_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(nzval_out, P.nzval.p, (size_t)P.nnz * 8, cudaMemcpyDefault, C->stream));
     if (b_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b_out, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
-    return finish_timing(C);
+    return finish_timing(C, nzval_out != nullptr || b_out != nullptr);
 }
 
 int extfem_quadrature_points(extfem_ctx *ctx, int pattern, const extfem_opdesc *d, int is_linear, int *nq_out, double *xq)

@@ -162,7 +162,10 @@ int extfem_pattern_dims(extfem_ctx *ctx, int pattern, int64_t *nrows, int64_t *n
 int extfem_pattern_get(extfem_ctx *ctx, int pattern, int64_t *colptr /*[ncols+1]*/, int64_t *rowval /*[nnz]*/);
 
 /* ---- assembly.  accumulate == 0 first zeroes the device values (fill!(nzval,0),
- *      src/solvers.jl:130-135); out pointers may be NULL (values stay device-resident).      */
+ *      src/solvers.jl:130-135); out pointers may be NULL (values stay device-resident).  A call that copies results into
+ *      caller memory returns when the copy is complete; a call whose results stay device-resident returns as soon as its
+ *      kernels are enqueued on the context's stream (later extfem_* calls are ordered behind them; extfem_synchronize,
+ *      extfem_last_timings and every call that returns data wait).                           */
 int extfem_assemble_bilinear(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, const double *sol /* args */,
                              int accumulate, double *nzval_out);
 int extfem_assemble_linear(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, const double *sol /* args */,
