@@ -732,7 +732,7 @@ local_nonlinear_kernel3(const __grid_constant__ OpDev op, const __grid_constant_
     unsigned char *tb = reinterpret_cast<unsigned char *>(smem_d + (size_t)nwarp * wd);
     for (int i = threadIdx.x; i < T.tab_bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(tb)[i] = __ldg(reinterpret_cast<const uint4 *>(T.tab) + i);
     __syncthreads();
-    const unsigned char *c_n = tb + T.o_cn, *c_out = tb + T.o_cout, *r_n = tb + T.o_rn, *r_out = tb + T.o_rout;
+    const unsigned char *r_n = tb + T.o_rn, *r_out = tb + T.o_rout;
     const int *bgidx = reinterpret_cast<const int *>(tb + T.o_bgidx), *btidx = reinterpret_cast<const int *>(tb + T.o_btidx);
     const double *bgsc = reinterpret_cast<const double *>(tb + T.o_bgsc), *btsc = reinterpret_cast<const double *>(tb + T.o_btsc);
     const unsigned short *gjj = reinterpret_cast<const unsigned short *>(tb + T.o_gjj), *gjb = reinterpret_cast<const unsigned short *>(tb + T.o_gjb);
