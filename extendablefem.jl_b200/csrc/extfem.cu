@@ -1,5 +1,6 @@
 // extfem.cu -- C-ABI implementation of libextfem_cuda.so (see include/extfem_cuda.h).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -13,6 +14,7 @@
 #include "pattern.cuh"
 #include "fastpath.cuh"
 #include "fastplan.cuh"
+#include "jit.cuh"
 #include "solver.cuh"
 #include "dist.cuh"
 
@@ -59,6 +61,10 @@ struct TemplatePlan {
     DevBuf wdesc, slotcol, slotpb, slotptr, tmpl, leftcols, dump;
     DevBuf cn_p, reg_p, vol_p;       // mesh arrays in the transposed cell order (Lg.permuted)
     long long vol_version = -1;
+    std::vector<JitTemplate> jtmpl;  // host copy of the templates (plan-time specialisation, jit.cuh)
+    std::unique_ptr<JitModule> jit;
+    DevBuf jit_live[2];              // launch-order warps of the short- / long-column class
+    int jit_nlive[2] = {0, 0};
 };
 
 struct Pattern {
@@ -114,6 +120,8 @@ struct Ctx {
     bool tmpl_enabled = true;   // option "fastpath_templates": 0 keeps every column on the record kernel
     int tmpl_ahead = 1024;      // option "template_prefetch_ctas": CTAs ahead whose start-up data is prefetched into L2
     int tmpl_pool = TP_POOL_BYTES; // option "template_pool_bytes": shared-memory pool of one template CTA
+    bool jit_enabled = false;   // option "template_jit": plan-time specialisation of the templates (jit.cuh); off by default
+    long long jit_mincols = 200000; // option "template_jit_min_cols": smallest column block that is worth the compile time
     bool tmpl_planemask = true; // option "template_plane_mask": rounds load only the geometry values their local column reads
     bool tmpl_const = true;     // option "template_constant_memory": template rounds in constant memory when they fit
     const void *const_tmpl_owner = nullptr;
@@ -798,6 +806,26 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
         T.ntemplates = 0;
         for (int g = 0; g < ngroups; ++g) T.ntemplates += hnw[g] > 0;
     }
+    {   // host copy of the templates: one entry per distinct first round
+        std::vector<unsigned> hwords((size_t)nrounds * TP_TW);
+        EXTFEM_CUDA_CHECK(ctx, cudaMemcpy(hwords.data(), T.tmpl.p, hwords.size() * 4, cudaMemcpyDeviceToHost));
+        std::map<int, std::pair<int, int>> seen;
+        for (int w = 0; w < nwarps; ++w) seen[hw[w].x] = std::make_pair(tp_desc_m(hw[w].y), tp_desc_L(hw[w].y));
+        T.jtmpl.clear();
+        for (auto &kv : seen) {
+            JitTemplate jt;
+            jt.r0 = kv.first; jt.m = kv.second.first; jt.L = kv.second.second;
+            jt.words.assign(hwords.begin() + (size_t)jt.r0 * TP_TW, hwords.begin() + (size_t)(jt.r0 + jt.m) * TP_TW);
+            T.jtmpl.push_back(std::move(jt));
+        }
+        std::vector<int> live[2];
+        for (size_t i = 0; i < launch.size(); ++i)
+            if (tp_desc_m(launch[i].y) > 0) live[tp_desc_L(launch[i].y) > JIT_SPLIT_L ? 1 : 0].push_back((int)i);
+        for (int c = 0; c < 2; ++c) {
+            T.jit_nlive[c] = (int)live[c].size();
+            if (!live[c].empty()) if (int rc = upload(ctx, T.jit_live[c], live[c].data(), live[c].size() * 4)) return rc;
+        }
+    }
     if (int rc = upload(ctx, T.wdesc, launch.data(), launch.size() * 16)) return rc;
     tp_affine_kernel<<<nblocks((long long)launch.size(), 8), 256, 0, st>>>((int)launch.size(), T.slotcol.as<int>(), T.slotptr.as<double *>(),
                                                                          T.wdesc.as<int4>());
@@ -934,7 +962,37 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
         perm ? T.vol_p.as<double>() : M.vol.as<double>(), d->factor * geoscale, d->nregions, ctx->visit.as<int>(), ctx->geo.as<double>(), T.Lg);
     LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    if (SOA && T.nwarps > 0) {
+    bool jit_done = false;
+    if (SOA && T.nwarps > 0 && EV::BARY && ctx->jit_enabled && T.ncols >= ctx->jit_mincols && !T.jtmpl.empty()) {
+        // plan-time specialisation of the templates (jit.cuh); any failure keeps the static kernel
+        if (!T.jit) T.jit = std::make_unique<JitModule>();
+        JitModule &J = *T.jit;
+        if (!J.tried) {
+            J.tried = true;
+            const auto t0 = std::chrono::steady_clock::now();
+            JitGen gen{EV::DIM_, EV::ORDER_, EV::NV, EV::NS};
+            bool present[2];
+            const std::string src = gen.source(T.jtmpl, JIT_SPLIT_L, present);
+            J.ok = jit_compile(src, present, J);
+            J.compile_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (!J.ok && getenv("EXTFEM_JIT_VERBOSE")) fprintf(stderr, "extfem: template specialisation failed: %s\n", J.log.c_str());
+        }
+        if (J.ok) {
+            JitArgs A;
+            A.wdesc = T.wdesc.as<int4>(); A.slotpb = T.slotpb.as<int>(); A.slotptr = T.slotptr.as<double *>();
+            A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate; A.nlive = 0; A.live = nullptr;
+            void *args[] = {&A};
+            for (int c = 1; c >= 0; --c) {   // long columns first
+                if (!J.present[c] || T.jit_nlive[c] == 0) continue;
+                A.nlive = T.jit_nlive[c]; A.live = T.jit_live[c].as<int>();
+                EXTFEM_CUDA_CHECK(ctx, cudaLaunchKernel((const void *)J.kernel[c], dim3(nblocks(A.nlive, TP_MAXW)), dim3(TP_MAXW * 32), args,
+                                                        (size_t)TP_MAXW * (32 * TP_LD + 32) * 8, ctx->stream));
+                LAUNCHED(ctx);
+            }
+            jit_done = true;
+        }
+    }
+    if (SOA && T.nwarps > 0 && !jit_done) {
         // first-touch stores need: overwrite, and column segments that hold rows of this block only
         const bool first = !accumulate && P.rowspaces.size() == 1;
         // templates in constant memory when they fit (re-uploaded when another plan used the bank in between)
@@ -1442,6 +1500,8 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_prefetch_ctas")) { C->tmpl_ahead = value < 0 ? 0 : value; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_pool_bytes")) { C->tmpl_pool = std::min(std::max(value, 4096), 200 * 1024); return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_jit")) { C->jit_enabled = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_jit_min_cols")) { C->jit_mincols = value < 0 ? 0 : value; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_plane_mask")) { C->tmpl_planemask = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_constant_memory")) { C->tmpl_const = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_permute_mesh")) { C->tmpl_permute_mesh = value != 0; return EXTFEM_OK; }
@@ -1772,6 +1832,17 @@ int extfem_assemble_linear(extfem_ctx *ctx, int pattern, const extfem_opdesc *d,
     }
     if (b_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b_out, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
     return finish_timing(C, b_out != nullptr);
+}
+
+/* 1: the templates of the block run as plan-time specialised kernels (jit.cuh); 0: not (disabled, below the size
+ * threshold, not a closed-form operator, or not assembled yet); -1: specialisation was tried and failed (static kernel) */
+int extfem_plan_jit_status(extfem_ctx *ctx, int pattern, int block)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (block < 0 || block >= (int)P.tplans.size()) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_plan_jit_status: bad block");
+    if (!P.tplans[block] || !P.tplans[block]->jit || !P.tplans[block]->jit->tried) return 0;
+    return P.tplans[block]->jit->ok ? 1 : -1;
 }
 
 /* statistics of the fast-path plans of column block `block` (built on first use):

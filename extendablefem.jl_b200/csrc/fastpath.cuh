@@ -301,6 +301,8 @@ struct FastArgs {
 template <int NS_, int NG_, int NV_>
 struct EvalTable {
     static constexpr int NS = NS_, NG = NG_, NV = NV_;
+    static constexpr bool BARY = false;          // no plan-time specialisation (jit.cuh)
+    static constexpr int DIM_ = NV_ - 1, ORDER_ = 0;
     // rows that EVERY adjacent cell of a column contributes to can be accumulated in registers (fastplan: template kernel):
     // slot of local row t for a column with local index kl, -1: none.  Any element: the column dof itself.
     static constexpr int NCOMMON = 1;
@@ -323,6 +325,8 @@ struct EvalTable {
 template <int DIM, int ORDER>
 struct EvalBary {
     static constexpr int NV = DIM + 1, NS = ORDER == 1 ? DIM + 1 : (DIM + 1) * (DIM + 2) / 2, NG = DIM * (DIM + 1) / 2;
+    static constexpr bool BARY = true;           // closed form: can be specialised per template at plan time (jit.cuh)
+    static constexpr int DIM_ = DIM, ORDER_ = ORDER;
     // geometry values (bit g = pair index of D_ab) that local column kl reads: the closed form only touches rows of the Gram
     // matrix that belong to the column dof's vertices (the vertex itself, or the two end points of its edge)
     __host__ __device__ static constexpr unsigned plane_mask(int kl)

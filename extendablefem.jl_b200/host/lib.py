@@ -22,7 +22,7 @@ EXPORTS = [
     "extfem_space_set", "extfem_space_set_tables", "extfem_pattern_build", "extfem_pattern_dims",
     "extfem_pattern_get", "extfem_assemble_bilinear", "extfem_assemble_linear", "extfem_assemble_nonlinear",
     "extfem_quadrature_points", "extfem_values_get", "extfem_values_set", "extfem_device_ptrs",
-    "extfem_apply_penalties", "extfem_residual", "extfem_spmv", "extfem_cg", "extfem_plan_stats",
+    "extfem_apply_penalties", "extfem_residual", "extfem_spmv", "extfem_cg", "extfem_plan_stats", "extfem_plan_jit_status",
     "extfem_dist_unique_id", "extfem_dist_init", "extfem_dist_set_interfaces", "extfem_dist_sum_rhs", "extfem_dist_spmv", "extfem_dist_cg",
 ]
 
@@ -279,6 +279,9 @@ class Engine:
         self._check(self.lib.extfem_plan_stats(self.ctx, pattern, block, st))
         keys = ["period", "templates", "template_warps", "record_columns", "template_ctas", "pool_bytes", "template_rounds", "columns"]
         return dict(zip(keys, [int(v) for v in st]))
+
+    def plan_jit_status(self, pattern: int, block: int = 0) -> int:
+        return int(self.lib.extfem_plan_jit_status(self.ctx, pattern, block))
 
     # ---- multi-GPU (one process per GPU) ------------------------------------------------------------
     @staticmethod

@@ -176,6 +176,9 @@ int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc 
  * { period P of the geometry order, templates, template warps, columns on the record kernel, CTAs of the template
  *   kernel, shared-memory pool bytes, template rounds, columns of the block }                                    */
 int extfem_plan_stats(extfem_ctx *ctx, int pattern, int block, int64_t *stats8);
+/* 1: the block's templates run as kernels specialised at plan time (NVRTC, sm_100a; options "template_jit",
+ * "template_jit_min_cols"), 0: they do not, -1: specialisation failed and the static template kernel is used */
+int extfem_plan_jit_status(extfem_ctx *ctx, int pattern, int block);
 /* x at the quadrature points the operator will use: xq[ncells][nq][dim]; *nq_out = nq.
  * xq may be NULL to query nq only.  (Host evaluates its closure there -> EXTFEM_LIN_TABULATED.) */
 int extfem_quadrature_points(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, int is_linear, int *nq_out,

@@ -157,6 +157,47 @@ def test_template_path(pkg, ora, engine, dim, order, n, permute):
         engine.set_option("template_min_cols", 24)
 
 
+@pytest.mark.parametrize("dim,order,n,permute", [(3, 2, 7, False), (3, 2, 6, True), (3, 1, 8, False), (2, 2, 12, True), (2, 1, 12, False)])
+def test_template_specialised_kernels(pkg, ora, engine, dim, order, n, permute):
+    """Plan-time specialisation of the templates (NVRTC): same sums as the static template kernel and the oracle; overwrite,
+    accumulate, regions."""
+    X = np.linspace(0, 1, n + 1)
+    g = pkg.simplexgrid(*([X] * dim))
+    g.cellregions[1::5] = 2
+    if permute:
+        cn = g.cellnodes.copy()
+        for k, p in ((1, [1, 2, 0]), (2, [2, 0, 1])):
+            sel = np.arange(g.ncells) % 3 == k
+            cn[sel, :3] = g.cellnodes[sel][:, p]
+        g.cellnodes[:] = cn
+        g._cache.clear()
+    engine.set_option("template_min_cols", 2)
+    engine.set_option("template_jit_min_cols", 0)
+    engine.set_option("template_jit", 1)
+    try:
+        S = System(pkg, ora, engine, g, [pkg.H1Pk(1, dim, order)])
+        for regions in ((), (1,)):
+            desc = engine.make_opdesc([(0, GRAD)], [(0, GRAD)], factor=0.75, regions=regions)
+            a = np.empty(S.rowval.size); b = np.empty(S.rowval.size)
+            engine.assemble_bilinear(S.pat, desc, nzval_out=a)
+            assert engine.plan_jit_status(S.pat, 0) == 1, "specialised kernels were not built"
+            ref = ora.assemble_bilinear(S.omesh, S.oargs([(0, GRAD)]), S.oargs([(0, GRAD)]), factor=0.75, regions=list(regions),
+                                        csc=(S.colptr, S.rowval))
+            check_values(a, ref, what="specialised vs oracle")
+            engine.assemble_bilinear(S.pat, desc, accumulate=True, nzval_out=b)
+            check_values(b, 2 * ref, what="specialised accumulate")
+            engine.set_option("template_jit", 0)
+            try:
+                engine.assemble_bilinear(S.pat, desc, nzval_out=b)
+            finally:
+                engine.set_option("template_jit", 1)
+            check_values(a, b, rtol=1e-13, what="specialised vs static template kernel")
+    finally:
+        engine.set_option("template_jit", 0)
+        engine.set_option("template_min_cols", 24)
+        engine.set_option("template_jit_min_cols", 200000)
+
+
 def test_template_path_block_system(pkg, ora, engine):
     """Two-block pattern (u, p): the Laplace fast path on block 0 must leave the other blocks' rows zero (no first-touch
     stores there) and the fast RHS must zero the other row blocks."""
