@@ -168,15 +168,15 @@ struct JitGen {
         std::ostringstream o;
         o << "struct JitArgs { const int4* wdesc; const int* slotpb; double* const* slotptr; const double* geo; long long Npad; int overwrite; int nlive; const int* live; };\n"
           << "// column j of the warp gets positions [p0, p0 + cnt) from the tile acc[position - p0][column] (leading dimension " << TP_LD << ")\n"
-          << "static __device__ __forceinline__ void wout(const double* acc, double* const* ptrs, double* gptr, int dw, int lane, int p0, int cnt, int overwrite) {\n"
+          << "static __device__ __noinline__ void wout(const double* acc, double* const* ptrs, double* gptr, int dw, int lane, int p0, int cnt, int overwrite) {\n"
           << "  const bool pin = lane < cnt;\n"
           << "  const double* src = acc + lane * " << TP_LD << ";\n"
           << "  if (dw) {\n"
           << "    double* q = (double*)__shfl_sync(0xffffffffu, (unsigned long long)gptr, 0) + p0 + lane;\n"
-          << "    #pragma unroll\n"
+          << "    #pragma unroll 8\n"
           << "    for (int j = 0; j < 32; ++j) { double v = src[j]; double* qq = q + (long long)j * dw; if (pin) { if (!overwrite) v += *qq; __stcs(qq, v); } }\n"
           << "  } else {\n"
-          << "    #pragma unroll\n"
+          << "    #pragma unroll 8\n"
           << "    for (int j = 0; j < 32; ++j) { double* qq = ptrs[j] + p0 + lane; double v = src[j]; if (pin) { if (!overwrite) v += *qq; __stcs(qq, v); } }\n"
           << "  }\n"
           << "}\n";
