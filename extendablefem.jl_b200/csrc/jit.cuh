@@ -84,40 +84,40 @@ struct JitGen {
     static int edge_b(int dim, int e) { return dim == 1 ? 1 : (dim == 2 ? (e + 1) % 3 : (e < 3 ? e + 1 : (e < 5 ? e - 1 : 3))); }
     int pair_index(int a, int b) const { return a * (2 * dim + 1 - a) / 2 + (b - a - 1); }
     // symbol of M[x][y]; records what the round needs
-    std::string M(int x, int y, unsigned &planes, unsigned &diags) const
+    std::string M(int x, int y, unsigned &planes, unsigned &diags, const std::string &R) const
     {
-        if (x == y) { diags |= 1u << x; return "d" + std::to_string(x); }
+        if (x == y) { diags |= 1u << x; return R + "d" + std::to_string(x); }
         const int p = pair_index(std::min(x, y), std::max(x, y));
         planes |= 1u << p;
-        return "g" + std::to_string(p);
+        return R + "g" + std::to_string(p);
     }
     // statements that add A_loc[t][kl] to accumulator `acc` (mirrors fp_bary_acc term by term)
-    void entry(std::ostringstream &o, const std::string &acc, int t, int kl, unsigned &planes, unsigned &diags) const
+    void entry(std::ostringstream &o, const std::string &acc, int t, int kl, unsigned &planes, unsigned &diags, const std::string &R) const
     {
         auto fma = [&](double c, const std::string &m) { o << acc << " = fma(" << c << ".0, " << m << ", " << acc << "); "; };
         auto sub = [&](const std::string &m) { o << acc << " -= " << m << "; "; };
-        if (order == 1) { o << acc << " += " << M(t, kl, planes, diags) << "; "; return; }
+        if (order == 1) { o << acc << " += " << M(t, kl, planes, diags, R) << "; "; return; }
         const bool tv = t < nv, kv = kl < nv;
         if (tv && kv) {
-            if (t == kl) fma(3, M(t, t, planes, diags)); else sub(M(t, kl, planes, diags));
+            if (t == kl) fma(3, M(t, t, planes, diags, R)); else sub(M(t, kl, planes, diags, R));
             return;
         }
         if (tv != kv) {
             const int i = tv ? t : kl, e = (tv ? kl : t) - nv, a = edge_a(dim, e), b = edge_b(dim, e);
             if (dim == 3) {
-                if (i == a) fma(3, M(i, b, planes, diags)); else sub(M(i, b, planes, diags));
-                if (i == b) fma(3, M(i, a, planes, diags)); else sub(M(i, a, planes, diags));
+                if (i == a) fma(3, M(i, b, planes, diags, R)); else sub(M(i, b, planes, diags, R));
+                if (i == b) fma(3, M(i, a, planes, diags, R)); else sub(M(i, a, planes, diags, R));
             } else {
-                if (i == a) fma(4, M(i, b, planes, diags));
-                if (i == b) fma(4, M(i, a, planes, diags));
+                if (i == a) fma(4, M(i, b, planes, diags, R));
+                if (i == b) fma(4, M(i, a, planes, diags, R));
             }
             return;
         }
         const int a = edge_a(dim, t - nv), b = edge_b(dim, t - nv), c = edge_a(dim, kl - nv), d = edge_b(dim, kl - nv);
-        fma(a == c ? 8 : 4, M(b, d, planes, diags));
-        fma(a == d ? 8 : 4, M(b, c, planes, diags));
-        fma(b == c ? 8 : 4, M(a, d, planes, diags));
-        fma(b == d ? 8 : 4, M(a, c, planes, diags));
+        fma(a == c ? 8 : 4, M(b, d, planes, diags, R));
+        fma(a == d ? 8 : 4, M(b, c, planes, diags, R));
+        fma(b == c ? 8 : 4, M(a, d, planes, diags, R));
+        fma(b == d ? 8 : 4, M(a, c, planes, diags, R));
     }
     void template_function(std::ostringstream &o, const JitTemplate &T, int id) const
     {
@@ -126,14 +126,18 @@ struct JitGen {
         o << "  double ";
         for (int p = 0; p < T.L; ++p) o << (p ? ", " : "") << "a" << p << " = 0.0";
         o << ";\n";
+        // per round: block A = loads of the geometry planes the round reads (named per round), block B = the entries.
+        // Emission order A0 A1 B0 A2 B1 ...: the loads of the next round are in flight during the current one.
+        std::vector<std::string> A(T.m), B(T.m);
         for (int r = 0; r < T.m; ++r) {
             const unsigned *w = &T.words[(size_t)r * TP_TW];
             const int pd = (int)w[0], kl = (int)(w[1] & 0xff);
+            const std::string R = "r" + std::to_string(r) + "_";
             std::ostringstream body;
             unsigned planes = 0, diags = 0;
             for (int t = 0; t < ns; ++t) {
                 const int pos = (int)(w[2 + t] / (TP_LD * 8));
-                entry(body, "a" + std::to_string(pos), t, kl, planes, diags);
+                entry(body, "a" + std::to_string(pos), t, kl, planes, diags, R);
                 body << "\n    ";
             }
             // diagonals need every plane that touches their vertex
@@ -141,19 +145,27 @@ struct JitGen {
                 if (diags >> x & 1)
                     for (int y = 0; y <= dim; ++y)
                         if (y != x) planes |= 1u << pair_index(std::min(x, y), std::max(x, y));
-            o << "  { const int i = pb + (" << pd << ");\n    ";
+            std::ostringstream la, lb;
+            la << "  const double* " << R << "p = geo + (pb + (" << pd << "));\n  ";
             for (int p = 0; p < dim * (dim + 1) / 2; ++p)
-                if (planes >> p & 1) o << "const double g" << p << " = __ldg(geo + " << p << " * Npad + i); ";
-            o << "\n    ";
+                if (planes >> p & 1) la << "const double " << R << "g" << p << " = __ldg(" << R << "p + " << p << " * Npad); ";
+            la << "\n";
+            lb << "  { ";
             for (int x = 0; x <= dim; ++x)
                 if (diags >> x & 1) {
-                    o << "const double d" << x << " = -(";
+                    lb << "const double " << R << "d" << x << " = -(";
                     bool first = true;
                     for (int y = 0; y <= dim; ++y)
-                        if (y != x) { o << (first ? "" : " + ") << "g" << pair_index(std::min(x, y), std::max(x, y)); first = false; }
-                    o << "); ";
+                        if (y != x) { lb << (first ? "" : " + ") << R << "g" << pair_index(std::min(x, y), std::max(x, y)); first = false; }
+                    lb << "); ";
                 }
-            o << "\n    " << body.str() << "}\n";
+            lb << "\n    " << body.str() << "}\n";
+            A[r] = la.str(); B[r] = lb.str();
+        }
+        o << A[0];
+        for (int r = 0; r < T.m; ++r) {
+            if (r + 1 < T.m) o << A[r + 1];
+            o << B[r];
         }
         // transposing write-out in slices of 32 positions through the warp's [32][33] shared tile
         for (int p0 = 0; p0 < T.L; p0 += 32) {
@@ -183,7 +195,7 @@ struct JitGen {
         for (size_t k = 0; k < tmpls.size(); ++k) template_function(o, tmpls[k], (int)k);
         present[0] = present[1] = false;
         for (int cls = 0; cls < 2; ++cls) {
-            o << "extern \"C\" __global__ void __launch_bounds__(" << TP_MAXW * 32 << ") tpj_" << cls << "(const JitArgs A) {\n"
+            o << "extern \"C\" __global__ void __launch_bounds__(" << TP_MAXW * 32 << ", " << (cls == 0 ? 4 : 3) << ") tpj_" << cls << "(const JitArgs A) {\n"
               << "  extern __shared__ double sm[];\n"
               << "  const int lane = threadIdx.x & 31, wi = blockIdx.x * " << TP_MAXW << " + (threadIdx.x >> 5);\n"
               << "  if (wi >= A.nlive) return;\n"

@@ -125,7 +125,9 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value);
  * record kernel, "template_min_cols" (24): smallest group of structurally identical columns that gets a template,
  * "template_pool_bytes" (37376), "template_prefetch_ctas" (1024), "template_constant_memory" (1),
  * "template_permute_mesh" (1): tuning knobs of the template kernel,
- * "nonlinear_kernel" (3): local kernel of NonlinearOperator, 1 entry-wise | 2 staged per block | 3 warp per cell */
+ * "nonlinear_kernel" (3): local kernel of NonlinearOperator, 1 entry-wise | 2 staged per block | 3 warp per cell,
+ * "template_jit" (0) / "template_jit_min_cols" (200000): experimental plan-time specialisation of the templates through
+ * NVRTC (jit.cuh), "template_plane_mask" (1) */
 /* number of kernel launches issued by this context since creation (bench "gpu_launches") */
 int64_t extfem_launch_count(extfem_ctx *ctx);
 /* device time in ms of the phases of the last assemble call (CUDA events):
