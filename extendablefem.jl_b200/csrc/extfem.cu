@@ -821,6 +821,14 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
         std::vector<int> live[2];
         for (size_t i = 0; i < launch.size(); ++i)
             if (tp_desc_m(launch[i].y) > 0) live[tp_desc_L(launch[i].y) > JIT_SPLIT_L ? 1 : 0].push_back((int)i);
+        // CTAs of one template: inside windows of 256 warps of the sweep (the same mesh neighbourhood, so that the interleaved
+        // output columns still merge in L2) the warps are grouped by template -- the 4 warps of a CTA then run the same
+        // straight-line code and fetch it once
+        for (int c = 0; c < 2; ++c)
+            for (size_t i0 = 0; i0 < live[c].size(); i0 += 256) {
+                const size_t i1 = std::min(live[c].size(), i0 + 256);
+                std::stable_sort(live[c].begin() + i0, live[c].begin() + i1, [&](int x, int y) { return launch[x].x < launch[y].x; });
+            }
         for (int c = 0; c < 2; ++c) {
             T.jit_nlive[c] = (int)live[c].size();
             if (!live[c].empty()) if (int rc = upload(ctx, T.jit_live[c], live[c].data(), live[c].size() * 4)) return rc;
