@@ -5,6 +5,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <set>
 #include <tuple>
 
 #include "common.cuh"
@@ -124,7 +125,6 @@ struct Ctx {
     long long jit_mincols = 200000; // option "template_jit_min_cols": smallest column block that is worth the compile time
     bool tmpl_planemask = true; // option "template_plane_mask": rounds load only the geometry values their local column reads
     bool tmpl_const = true;     // option "template_constant_memory": template rounds in constant memory when they fit
-    const void *const_tmpl_owner = nullptr;
     bool tmpl_permute_mesh = true; // option "template_permute_mesh": cell kernels read mesh copies in the transposed order
     int tmpl_mincols = 24;      // option "template_min_cols": smallest group of columns that gets a template
     bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator
@@ -133,7 +133,6 @@ struct Ctx {
     cudaEvent_t uev[16] = {};
     double last_ms[3] = {0, 0, 0};
     bool timing_pending = false;
-    const void *planemask_owner = nullptr;
 };
 
 static std::string g_last_error;
@@ -149,6 +148,22 @@ static int fail(Ctx *ctx, int code, const std::string &msg)
 {
     set_error(ctx, code, msg);
     return code;
+}
+
+// Kernel attributes and __constant__ banks are per DEVICE, not per context: remember per device what was set / who
+// owns the constant-memory copies, so that several contexts (also on different devices) can live in one process.
+constexpr int EXTFEM_MAXDEV = 64;
+static std::set<const void *> g_smem_attr_done[EXTFEM_MAXDEV];
+static const void *g_const_tmpl_owner[EXTFEM_MAXDEV] = {};
+static const void *g_planemask_owner[EXTFEM_MAXDEV] = {};
+
+static int smem_attr(Ctx *ctx, const void *kernel, int bytes)
+{
+    auto &done = g_smem_attr_done[ctx->device % EXTFEM_MAXDEV];
+    if (done.count(kernel)) return 0;
+    EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert(kernel);
+    return 0;
 }
 
 static int ensure(Ctx *ctx, DevBuf &b, size_t bytes)
@@ -943,11 +958,7 @@ static int launch_template(Ctx *ctx, Pattern &P, TemplatePlan &T, int b, int acc
     A.nwarps = T.nctas * TP_MAXW; A.ahead = ctx->tmpl_ahead * TP_MAXW;
     (void)P; (void)b;
     auto k = tp_gather_kernel<EV, FIRST, CT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    if (int rc = smem_attr(ctx, (const void *)k, 227 * 1024)) return rc;
     k<<<T.nctas, TP_MAXW * 32, T.pool_bytes, ctx->stream>>>(A);
     LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
@@ -1005,19 +1016,19 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
         const bool first = !accumulate && P.rowspaces.size() == 1;
         // templates in constant memory when they fit (re-uploaded when another plan used the bank in between)
         const bool ct = ctx->tmpl_const && T.nrounds <= TP_CONST_ROUNDS;
-        if (ct && ctx->const_tmpl_owner != &T) {
+        if (ct && g_const_tmpl_owner[ctx->device % EXTFEM_MAXDEV] != &T) {
             EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_tmpl, T.tmpl.p, (size_t)T.nrounds * TP_TW * 4, 0, cudaMemcpyDeviceToDevice, ctx->stream));
-            ctx->const_tmpl_owner = &T;
+            g_const_tmpl_owner[ctx->device % EXTFEM_MAXDEV] = &T;
         }
         {
             static const char ev_tag = 0;   // one per evaluator instantiation
             const void *owner = ctx->tmpl_planemask ? (const void *)&ev_tag : (const void *)ctx;
-            if (ctx->planemask_owner != owner) {
+            if (g_planemask_owner[ctx->device % EXTFEM_MAXDEV] != owner) {
                 unsigned pm[16];
                 for (int kl = 0; kl < 16; ++kl) pm[kl] = ctx->tmpl_planemask ? EV::plane_mask(kl < EV::NS ? kl : 0) : (1u << EV::NG) - 1u;
                 EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_planemask, pm, sizeof(pm), 0, cudaMemcpyHostToDevice, ctx->stream));
                 EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // pm lives on the stack
-                ctx->planemask_owner = owner;
+                g_planemask_owner[ctx->device % EXTFEM_MAXDEV] = owner;
             }
         }
         int rc;
@@ -1039,13 +1050,9 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
         auto k0 = fp_gather_kernel<EV, 1, 6, SOA>;
         auto k1 = fp_gather_kernel<EV, NGRP_BIG, (NGRP_BIG == 2 ? 3 : 4), SOA>;
         auto k2 = fp_gather_kernel<EV, NGRP_BIG, 3, SOA>;
-        static bool attr_set = false;
-        if (!attr_set) {
-            EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
-            EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
-            EXTFEM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, fp_cap(FP_NCLASS - 1) * 8));
-            attr_set = true;
-        }
+        if (int rc = smem_attr(ctx, (const void *)k0, fp_cap(FP_NCLASS - 1) * 8)) return rc;
+        if (int rc = smem_attr(ctx, (const void *)k1, fp_cap(FP_NCLASS - 1) * 8)) return rc;
+        if (int rc = smem_attr(ctx, (const void *)k2, fp_cap(FP_NCLASS - 1) * 8)) return rc;
         for (int c = FP_NCLASS - 1; c >= 0; --c) { // longest-running class first
             int n = F.cls_start[c + 1] - F.cls_start[c];
             if (n == 0) continue;
@@ -1463,6 +1470,8 @@ int extfem_ctx_destroy(extfem_ctx *ctx)
     for (auto &ev : C->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : C->uev) if (ev) cudaEventDestroy(ev);
     C->patterns.clear(); C->spaces.clear(); C->meshes.clear();
+    g_const_tmpl_owner[C->device % EXTFEM_MAXDEV] = nullptr;   // plans of this context may have owned the constant banks
+    g_planemask_owner[C->device % EXTFEM_MAXDEV] = nullptr;
     if (C->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(C->dist.comm);
     cudaStream_t s = C->stream;
     delete C;
@@ -1903,8 +1912,7 @@ int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc 
             while (nw > 1 && (size_t)nw * wd * 8 + T3.tab_bytes > 100 * 1024) nw >>= 1;
             const size_t smem = (size_t)nw * wd * 8 + T3.tab_bytes;
             if (smem <= 200 * 1024) {
-                static bool attr_set3 = false;
-                if (!attr_set3) { cudaFuncSetAttribute(local_nonlinear_kernel3<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set3 = true; }
+                smem_attr(C, (const void *)local_nonlinear_kernel3<DIM>, 200 * 1024);
                 const int cpw = 4;   // cells per warp: amortises the table load of a block
                 local_nonlinear_kernel3<DIM><<<nblocks(op.ncells, nw * cpw), nw * 32, smem, C->stream>>>(op, T3, C->loc.as<double>(),
                                                                                                       C->bloc.as<double>(), cpw);
@@ -1914,8 +1922,7 @@ int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc 
         if (v2) {
             const size_t per_cell = nl2_cell_bytes((int)sizeof(CellGeo<DIM>), op.nq, op.nin, op.nout, op.NR, op.NC);
             const int cpb = (int)std::max<size_t>(1, std::min<size_t>(8, (72 * 1024) / per_cell));
-            static bool attr_set = false;
-            if (!attr_set) { cudaFuncSetAttribute(local_nonlinear_kernel2<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+            smem_attr(C, (const void *)local_nonlinear_kernel2<DIM>, 200 * 1024);
             local_nonlinear_kernel2<DIM><<<nblocks(op.ncells, cpb), 256, cpb * per_cell, C->stream>>>(op, C->loc.as<double>(),
                                                                                                     C->bloc.as<double>(), cpb);
             return;

@@ -29,7 +29,9 @@
  *  - the sparsity pattern is STRUCTURAL (dofs sharing a cell, filtered by the block coupling);
  *    the reference's value-dependent pattern (entries exactly 0.0 are never inserted,
  *    bilinear_operator.jl:925) is always a subset of it.
- *  - a context is not re-entrant; calls on one context are serialised by the caller.
+ *  - a context is not re-entrant; calls on one context are serialised by the caller.  Several contexts may live in one
+ *    process (one per device, or several on one device used one after the other); contexts on the SAME device must not
+ *    run concurrently (they share the device's __constant__ tables).
  *  - there is no CPU fallback: without a CUDA device extfem_ctx_create fails.
  */
 #ifndef EXTFEM_CUDA_H
