@@ -150,7 +150,8 @@ static inline int dist_jacobi_cg(cudaStream_t st, DistState &D, IfacePlan &I, lo
                                  SolverWork &W, long long *launches, std::string *err)
 {
     if (W.n_alloc < n) {
-        for (auto &v : W.vec) { if (v) cudaFree(v); if (cudaMalloc(&v, n * 8)) return -1; }
+        W.n_alloc = 0;
+        for (auto &v : W.vec) { if (v) { cudaFree(v); v = nullptr; } if (cudaMalloc(&v, n * 8)) { v = nullptr; return -1; } }
         if (!W.partial && cudaMalloc(&W.partial, RED_BLOCKS * 8)) return -1;
         if (!W.scalars && cudaMalloc(&W.scalars, 8 * 8)) return -1;
         W.n_alloc = n;

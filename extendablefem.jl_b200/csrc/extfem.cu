@@ -18,6 +18,7 @@
 #include "jit.cuh"
 #include "solver.cuh"
 #include "dist.cuh"
+#include "entities.cuh"
 
 namespace extfem {
 
@@ -29,20 +30,28 @@ struct DevBuf {
 };
 
 struct Mesh {
-    int dim = 0;
+    int dim = 0;                     // space dimension
+    int tdim = 0;                    // topological dimension of the items (== dim for cells, dim - 1 for boundary faces)
     long long ncells = 0, nnodes = 0;
-    DevBuf coords, cellnodes, regions, vol, geo;
-    bool geo_valid = false;
+    DevBuf coords, cellnodes, regions, vol;
     long long vol_version = 0;       // bumped when the cell volumes change
+    Mesh *parent = nullptr;          // boundary-face meshes borrow the coordinates of their grid
+    std::unique_ptr<Mesh> bf;        // xgrid[BFaceNodes / BFaceRegions / BFaceVolumes] (extfem_mesh_set_bfaces)
+    bool bf_vol_given = false;
+    double *coordsp() const { return parent ? parent->coords.as<double>() : coords.as<double>(); }
 };
 
 struct Space {
+    int id = -1;                     // index in Ctx::spaces
+    int tabkey = -1;                 // table cache key of a host-supplied basis (2 * id + face), -1: built-in
     int mesh = -1, fetype = 0, order = 0, ncomp = 0, nscalar = 0, nd = 0;
     long long ndofs = 0;
     DevBuf celldofs, adjptr, adjcell, adjloc;
-    // host-supplied tables (EXTFEM_FE_TABULATED)
-    int tab_nq = 0;
-    DevBuf tab_vals, tab_grads;
+    // host-supplied polynomial reference basis (EXTFEM_FE_TABULATED, extfem_space_set_tables)
+    bool poly_ready = false;
+    std::vector<double> poly, bpoly; // [nscalar][nmono(order, tdim)], boundary-face restriction [nscalar_bf][nmono(order, tdim-1)]
+    int nscalar_bf = 0;
+    std::unique_ptr<Space> bf;       // FES[BFaceDofs] (extfem_space_set_bfacedofs): item dof map over the boundary faces
 };
 
 struct FastPlan {
@@ -90,8 +99,8 @@ struct Pattern {
 };
 
 struct TableKey {
-    int dim, order, quadorder;
-    bool operator<(const TableKey &o) const { return std::tie(dim, order, quadorder) < std::tie(o.dim, o.order, o.quadorder); }
+    int dim, order, quadorder, space;   // space >= 0: host-supplied basis of that space (2 * id + face)
+    bool operator<(const TableKey &o) const { return std::tie(dim, order, quadorder, space) < std::tie(o.dim, o.order, o.quadorder, o.space); }
 };
 struct DevTables {
     int nq = 0;
@@ -157,6 +166,14 @@ static std::set<const void *> g_smem_attr_done[EXTFEM_MAXDEV];
 static const void *g_const_tmpl_owner[EXTFEM_MAXDEV] = {};
 static const void *g_planemask_owner[EXTFEM_MAXDEV] = {};
 
+// Contexts on one device share the __constant__ tables (templates, plane masks, reference tables).  Every launch that
+// reads them records an event; an upload by ANOTHER context first makes its stream wait for that event, so a context can
+// never overwrite tables a kernel of the other context is still reading (contexts used alternately without synchronize).
+static const void *g_const_last_ctx[EXTFEM_MAXDEV] = {};
+static cudaEvent_t g_const_ev[EXTFEM_MAXDEV] = {};
+static int const_acquire(Ctx *ctx);
+static int const_release(Ctx *ctx);
+
 static int smem_attr(Ctx *ctx, const void *kernel, int bytes)
 {
     auto &done = g_smem_attr_done[ctx->device % EXTFEM_MAXDEV];
@@ -178,6 +195,23 @@ static int ensure(Ctx *ctx, DevBuf &b, size_t bytes)
 
 static inline unsigned nblocks(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+static int const_acquire(Ctx *ctx)
+{
+    const int d = ctx->device % EXTFEM_MAXDEV;
+    if (g_const_last_ctx[d] && g_const_last_ctx[d] != ctx && g_const_ev[d])
+        EXTFEM_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, g_const_ev[d], 0));
+    return 0;
+}
+
+static int const_release(Ctx *ctx)
+{
+    const int d = ctx->device % EXTFEM_MAXDEV;
+    if (!g_const_ev[d]) EXTFEM_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&g_const_ev[d], cudaEventDisableTiming));
+    EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(g_const_ev[d], ctx->stream));
+    g_const_last_ctx[d] = ctx;
+    return 0;
+}
+
 #define LAUNCHED(ctx) (++(ctx)->launches)
 
 // ---------------------------------------------------------------------------------------------
@@ -188,15 +222,20 @@ static int upload(Ctx *ctx, DevBuf &dst, const void *src, size_t bytes)
     return 0;
 }
 
-static int upload_indices(Ctx *ctx, DevBuf &dst, const void *src, int index_bytes, long long n)
+static int upload_indices(Ctx *ctx, DevBuf &dst, const void *src, int index_bytes, long long n, long long nmax, const char *what)
 {
-    // src may be host or device; stage raw bytes on the device, then convert to 0-based int32
-    DevBuf raw;
+    // src may be host or device; stage raw bytes on the device, then convert to 0-based int32 (range-checked: 1..nmax)
+    DevBuf raw, err;
     if (int rc = upload(ctx, raw, src, (size_t)n * index_bytes)) return rc;
     if (int rc = ensure(ctx, dst, (size_t)n * sizeof(int))) return rc;
-    convert_index_kernel<<<nblocks(n, 256), 256, 0, ctx->stream>>>(raw.p, index_bytes, n, dst.as<int>());
+    if (int rc = ensure(ctx, err, 4)) return rc;
+    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(err.p, 0, 4, ctx->stream));
+    convert_index_kernel<<<nblocks(n, 256), 256, 0, ctx->stream>>>(raw.p, index_bytes, n, nmax, dst.as<int>(), err.as<int>());
     LAUNCHED(ctx);
+    int herr = 0;
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(&herr, err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (herr) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, std::string(what) + ": index outside 1.." + std::to_string(nmax) + " (indices are 1-based)");
     return 0;
 }
 
@@ -255,13 +294,20 @@ static int get_quad(Ctx *ctx, int dim, int order, DevQuad **out)
     return 0;
 }
 
-static int get_tables(Ctx *ctx, int dim, int order, int quadkey, const QuadRule &Q, DevTables **out)
+// scalar reference basis of space S (built-in H1P1/H1P2 or host-supplied polynomials) at the points of Q
+static void space_ref_basis(const Space &S, int tdim, const QuadRule &Q, std::vector<double> &v, std::vector<double> &g)
 {
-    TableKey key{dim, order, quadkey};
+    if (S.fetype == EXTFEM_FE_TABULATED) poly_basis(S.order, tdim, S.nscalar, S.poly, Q, v, g);
+    else ref_basis(S.order, tdim, Q, v, g);
+}
+
+static int get_tables(Ctx *ctx, const Space &S, int dim, int quadkey, const QuadRule &Q, DevTables **out)
+{
+    TableKey key{dim, S.order, quadkey, S.tabkey};
     auto it = ctx->tables.find(key);
     if (it == ctx->tables.end() || quadkey < 0) {
         std::vector<double> v, g;
-        ref_basis(order, dim, Q, v, g);
+        space_ref_basis(S, dim, Q, v, g);
         auto dt = std::make_unique<DevTables>();
         dt->nq = Q.nq;
         if (int rc = upload(ctx, dt->vals, v.data(), v.size() * 8)) return rc;
@@ -291,16 +337,18 @@ struct Prepared {
     std::vector<int> testblocks, colblocks; // unique blocks (ascending)
     std::vector<int> testlocoff, collocoff;  // operator-local offsets of these blocks
     int quadorder = 0;
+    int entities = EXTFEM_ON_CELLS;
     QuadRule Q;                              // host copy of the operator's quadrature rule
 };
 
-enum OpKind { KIND_BILINEAR = 0, KIND_LINEAR = 1, KIND_NONLINEAR = 2 };
+enum OpKind { KIND_BILINEAR = 0, KIND_LINEAR = 1, KIND_NONLINEAR = 2, KIND_INTEGRATE = 3 };
 
 static bool kernel_known(int kind, int id)
 {
-    if (kind == KIND_BILINEAR) return id >= EXTFEM_BLK_STANDARD && id <= EXTFEM_BLK_CONVECT_ARGS;
-    if (kind == KIND_LINEAR) return id >= EXTFEM_LIN_CONSTANT_ONE && id <= EXTFEM_LIN_TABULATED;
-    return id >= EXTFEM_NL_NSE2D && id <= EXTFEM_NL_RCD;
+    if (kind == KIND_BILINEAR) return id >= EXTFEM_BLK_STANDARD && id <= EXTFEM_BLK_ROBIN108;
+    if (kind == KIND_LINEAR) return id >= EXTFEM_LIN_CONSTANT_ONE && id <= EXTFEM_LIN_STEP105;
+    if (kind == KIND_INTEGRATE) return id >= EXTFEM_II_STANDARD && id <= EXTFEM_II_L2ERR_EXP108;
+    return id >= EXTFEM_NL_NSE2D && id <= EXTFEM_NL_STVENANT230;
 }
 
 static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const double *sol, Prepared &R)
@@ -312,8 +360,14 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
     } else if (!kernel_known(kind, d->kernel_id))
         return fail(ctx, EXTFEM_ERR_UNREGISTERED_KERNEL,
                     "kernel id " + std::to_string(d->kernel_id) + " is not in the registry of this operator type");
-    if (d->ntest < 1 || d->ntest > MAXARGS || d->nansatz < 0 || d->nansatz > MAXARGS || d->nargs < 0 || d->nargs > MAXARGS)
+    if (d->ntest < (kind == KIND_INTEGRATE ? 0 : 1) || d->ntest > MAXARGS || d->nansatz < 0 || d->nansatz > MAXARGS || d->nargs < 0 ||
+        d->nargs > MAXARGS)
         return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "number of operator arguments out of range");
+    if (kind == KIND_INTEGRATE && d->nargs < 1) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "ItemIntegrator needs args");
+    const bool onbf = d->entities == EXTFEM_ON_BFACES;
+    if (d->entities != EXTFEM_ON_CELLS && !onbf) return fail(ctx, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "entities must be ON_CELLS or ON_BFACES");
+    if (onbf && (kind == KIND_NONLINEAR || kind == KIND_INTEGRATE))
+        return fail(ctx, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "ON_BFACES is built for BilinearOperator and LinearOperator only");
     if (kind == KIND_BILINEAR && d->nansatz < 1) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "BilinearOperator needs ansatz arguments");
     if (kind == KIND_NONLINEAR && d->nargs < 1) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "NonlinearOperator needs args");
     if (d->nparams > MAXPARAMS) return fail(ctx, EXTFEM_ERR_CAPACITY, "too many kernel parameters");
@@ -323,11 +377,14 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
     OpDev &op = R.op;
     memset(&op, 0, sizeof(op));
     Space &S0 = *ctx->spaces[P.rowspaces[0]];
-    Mesh &M = *ctx->meshes[S0.mesh];
+    Mesh &Mc = *ctx->meshes[S0.mesh];
+    if (onbf && !Mc.bf) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "ON_BFACES needs extfem_mesh_set_bfaces on the grid");
+    Mesh &M = onbf ? *Mc.bf : Mc;    // the item mesh: cells or boundary faces
     R.mesh = &M;
+    R.entities = d->entities;
     op.dim = M.dim;
     op.ncells = M.ncells;
-    op.coords = M.coords.as<double>();
+    op.coords = M.coordsp();
     op.cellnodes = M.cellnodes.as<int>();
     op.cellregions = M.regions.as<int>();
     op.cellvolumes = M.vol.as<double>();
@@ -344,23 +401,26 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
         for (int i = 0; i < d->nansatz * d->ntest; ++i) op.coupling[i] = d->coupling[i];
 
     // --- resolve spaces / polynomial orders
-    auto rowspace = [&](int b) -> Space * { return (b >= 0 && b < (int)P.rowspaces.size()) ? ctx->spaces[P.rowspaces[b]].get() : nullptr; };
-    auto colspace = [&](int b) -> Space * { return (b >= 0 && b < (int)P.colspaces.size()) ? ctx->spaces[P.colspaces[b]].get() : nullptr; };
+    // item spaces: the cell dof map, or FES[BFaceDofs] for ON_BFACES (nullptr when missing)
+    auto item = [&](Space *S) -> Space * { return S && onbf ? S->bf.get() : S; };
+    auto rowspace = [&](int b) -> Space * { return item((b >= 0 && b < (int)P.rowspaces.size()) ? ctx->spaces[P.rowspaces[b]].get() : nullptr); };
+    auto colspace = [&](int b) -> Space * { return item((b >= 0 && b < (int)P.colspaces.size()) ? ctx->spaces[P.colspaces[b]].get() : nullptr); };
+    const char *nospace = onbf ? "block index out of range or space without BFaceDofs (extfem_space_set_bfacedofs)" : "block index out of range";
     int poly_t = 0, poly_a = 0, poly_g = 0;
     auto poly = [&](Space *S, int o) { return S->order - (o == EXTFEM_OP_ID ? 0 : 1); };
     for (int i = 0; i < d->ntest; ++i) {
         Space *S = rowspace(d->test_block[i]);
-        if (!S) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "test block index out of range");
+        if (!S) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, std::string("test: ") + nospace);
         poly_t = std::max(poly_t, poly(S, d->test_op[i]));
     }
     for (int i = 0; i < d->nansatz; ++i) {
         Space *S = colspace(d->ansatz_block[i]);
-        if (!S) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "ansatz block index out of range");
+        if (!S) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, std::string("ansatz: ") + nospace);
         poly_a = std::max(poly_a, poly(S, d->ansatz_op[i]));
     }
     for (int i = 0; i < d->nargs; ++i) {
         Space *S = colspace(d->args_block[i]);
-        if (!S) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "args block index out of range");
+        if (!S) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, std::string("args: ") + nospace);
         poly_g = std::max(poly_g, poly(S, d->args_op[i]));
     }
     // quadrature order (bilinear_operator.jl:728-734, linear_operator.jl:534-538 / :299-305,
@@ -369,23 +429,24 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
     if (d->quadorder >= 0) qo = d->quadorder + d->bonus_quadorder;
     else if (kind == KIND_BILINEAR) qo = poly_a + poly_t + d->bonus_quadorder;
     else if (kind == KIND_LINEAR) qo = poly_t + (d->nargs > 0 ? poly_g : 0) + d->bonus_quadorder;
+    else if (kind == KIND_INTEGRATE) qo = poly_g + d->bonus_quadorder;                    // item_integrator.jl:147-151
     else qo = poly_g + poly_t + d->bonus_quadorder;
     R.quadorder = qo;
     QuadRule Q;
     int quadkey = qo;
     if (d->nq_custom > 0) {
         if (!d->qweights || !d->qpoints) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "custom quadrature needs weights and points");
-        Q.dim = M.dim; Q.nq = d->nq_custom;
+        Q.dim = M.tdim; Q.nq = d->nq_custom;
         Q.w.assign(d->qweights, d->qweights + Q.nq);
-        Q.x.assign(d->qpoints, d->qpoints + (size_t)Q.nq * M.dim);
+        Q.x.assign(d->qpoints, d->qpoints + (size_t)Q.nq * M.tdim);
         if (int rc = upload(ctx, ctx->custom_qw, Q.w.data(), Q.w.size() * 8)) return rc;
         if (int rc = upload(ctx, ctx->custom_qx, Q.x.data(), Q.x.size() * 8)) return rc;
         op.qw = ctx->custom_qw.as<double>(); op.qx = ctx->custom_qx.as<double>();
         quadkey = -1;
     } else {
         DevQuad *dq;
-        if (int rc = get_quad(ctx, M.dim, qo, &dq)) return rc;
-        Q.dim = M.dim; Q.nq = dq->nq; Q.w = dq->hw; Q.x = dq->hx;
+        if (int rc = get_quad(ctx, M.tdim, qo, &dq)) return rc;
+        Q.dim = M.tdim; Q.nq = dq->nq; Q.w = dq->hw; Q.x = dq->hx;
         op.qw = dq->w.as<double>(); op.qx = dq->x.as<double>();
     }
     op.nq = Q.nq;
@@ -395,7 +456,7 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
     auto uniq = [](std::vector<int> v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); return v; };
     std::vector<int> tb, cb;
     for (int i = 0; i < d->ntest; ++i) tb.push_back(d->test_block[i]);
-    if (kind == KIND_NONLINEAR) for (int i = 0; i < d->nargs; ++i) cb.push_back(d->args_block[i]);
+    if (kind == KIND_NONLINEAR || kind == KIND_INTEGRATE) for (int i = 0; i < d->nargs; ++i) cb.push_back(d->args_block[i]);
     else for (int i = 0; i < d->nansatz; ++i) cb.push_back(d->ansatz_block[i]);
     R.testblocks = uniq(tb);
     R.colblocks = uniq(cb);
@@ -409,10 +470,13 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
         return -1;
     };
     auto fill_arg = [&](ArgDev &a, Space *S, int o, int block, int &opoff, int locoff, long long soloff) -> int {
-        if (S->fetype != EXTFEM_FE_H1P1 && S->fetype != EXTFEM_FE_H1P2)
-            return fail(ctx, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "only H1P1/H1P2 (H1Pk order<=2) are built in");
+        if (S->fetype == EXTFEM_FE_TABULATED && !S->poly_ready)
+            return fail(ctx, EXTFEM_ERR_UNSUPPORTED_ELEMENT, onbf ? "host-tabulated space without a boundary-face basis (extfem_space_set_tables: bface_coeffs)"
+                                                                  : "host-tabulated space without a basis (extfem_space_set_tables)");
         if (o < EXTFEM_OP_ID || o > EXTFEM_OP_SYMGRAD_VOIGT)
             return fail(ctx, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "unsupported function operator");
+        if (onbf && o != EXTFEM_OP_ID)
+            return fail(ctx, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "ON_BFACES supports Identity operators only");
         a.ncomp = S->ncomp; a.nscalar = S->nscalar; a.op = o; a.nd = S->nd;
         a.oplen = oplen_of(o, S->ncomp, M.dim);
         a.opoff = opoff; opoff += a.oplen;
@@ -420,7 +484,7 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
         a.celldofs = S->celldofs.as<int>();
         a.soloff = soloff;
         DevTables *T;
-        if (int rc = get_tables(ctx, M.dim, S->order, quadkey, Q, &T)) return rc;
+        if (int rc = get_tables(ctx, *S, M.tdim, quadkey, Q, &T)) return rc;
         a.refvals = T->vals.as<double>(); a.refgrads = T->grads.as<double>();
         return 0;
     };
@@ -433,7 +497,7 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
                               locoff_of(R.colblocks, R.collocoff, d->ansatz_block[i]), 0)) return rc;
     for (int i = 0; i < d->nargs; ++i)
         if (int rc = fill_arg(op.args[i], colspace(d->args_block[i]), d->args_op[i], d->args_block[i], off_g,
-                              kind == KIND_NONLINEAR ? locoff_of(R.colblocks, R.collocoff, d->args_block[i]) : 0,
+                              (kind == KIND_NONLINEAR || kind == KIND_INTEGRATE) ? locoff_of(R.colblocks, R.collocoff, d->args_block[i]) : 0,
                               P.coloff[d->args_block[i]])) return rc;
     op.nout = off_t;
     op.nin = (kind == KIND_BILINEAR && d->nargs == 0) ? off_a : off_g;
@@ -446,6 +510,14 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
         return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "nse2d kernels need [id(u),grad(u),id(p)] in 2D");
     if (kind == KIND_NONLINEAR && d->kernel_id == EXTFEM_NL_NEOHOOKE3D && (off_g != 9 || off_t != 9 || M.dim != 3))
         return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "neohooke3d needs [grad(u)] in 3D");
+    if (kind == KIND_NONLINEAR && d->kernel_id == EXTFEM_NL_STVENANT230 &&
+        (off_g != 4 || off_t != 4 || M.dim != 2 || d->nparams < 4 || d->nparams != 1 + 3 * (int)d->params[0]))
+        return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "stvenant230 needs [grad(u)] in 2D and params R, lambda[R], mu[R], epsT[R]");
+    if (kind == KIND_NONLINEAR && (d->kernel_id == EXTFEM_NL_RCD || d->kernel_id == EXTFEM_NL_NLPOISSON105) &&
+        (off_g != 1 + M.dim || off_t != 1 + M.dim || (d->kernel_id == EXTFEM_NL_NLPOISSON105 && d->nparams < 1)))
+        return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "rcd / nlpoisson105 need [id(u), grad(u)] of a scalar unknown");
+    if (kind == KIND_BILINEAR && d->kernel_id == EXTFEM_BLK_ROBIN108 && (d->nparams < 1 || off_t != off_a))
+        return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "robin108 needs params g and equal operator lengths");
     if (sol) {
         if (int rc = upload(ctx, ctx->sol, sol, (size_t)P.ncols * 8)) return rc;
         op.sol = ctx->sol.as<double>();
@@ -455,6 +527,7 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
         if (int rc = upload(ctx, ctx->tab, d->tabulated, (size_t)M.ncells * op.nq * op.nout * 8)) return rc;
         op.tabulated = ctx->tab.as<double>();
     }
+    if (kind == KIND_INTEGRATE) op.tabulated = nullptr;   // uploaded by extfem_integrate (needs resultdim)
     return 0;
 }
 
@@ -1150,13 +1223,13 @@ static int try_fast_bilinear(Ctx *ctx, Pattern &P, const Prepared &R, const extf
     if (!ctx->fast_enabled) return 0;
     const OpDev &op = R.op;
     if (d->kernel_id != EXTFEM_BLK_STANDARD || d->ntest != 1 || d->nansatz != 1 || d->nargs != 0 || d->lump != 0 ||
-        d->transposed_copy != 0 || d->test_block[0] != d->ansatz_block[0])
+        d->transposed_copy != 0 || d->test_block[0] != d->ansatz_block[0] || d->entities != EXTFEM_ON_CELLS)
         return 0;
     const int b = d->test_block[0];
     if (b >= (int)P.colspaces.size() || b >= (int)P.rowspaces.size() || P.rowspaces[b] != P.colspaces[b]) return 0;
     if (!P.coupling[(size_t)b * P.rowspaces.size() + b] || P.poswidth != 1) return 0;
     Space &S = *ctx->spaces[P.colspaces[b]];
-    if (S.ncomp != 1 || S.nscalar > 10) return 0;
+    if (S.ncomp != 1 || S.nscalar > 10 || S.fetype == EXTFEM_FE_TABULATED) return 0;
     int form;
     if (d->test_op[0] == EXTFEM_OP_GRAD && d->ansatz_op[0] == EXTFEM_OP_GRAD) form = FP_FORM_LAPLACE;
     else if (d->test_op[0] == EXTFEM_OP_ID && d->ansatz_op[0] == EXTFEM_OP_ID) form = FP_FORM_MASS;
@@ -1176,6 +1249,7 @@ static int try_fast_bilinear(Ctx *ctx, Pattern &P, const Prepared &R, const extf
     const QuadRule &Q = R.Q;   // host copy kept by prepare(): no device round trip
     std::vector<double> T = fast_tables(Q, S.order, dim, form);
     int rc = -1;
+    if (int rca = const_acquire(ctx)) return rca;
     // closed-form barycentric evaluators (Laplace, P1/P2, 2D/3D), verified against the tables
     if (form == FP_FORM_LAPLACE && ctx->bary_enabled) {
 #define FP_BARY(D, O) \
@@ -1199,6 +1273,7 @@ static int try_fast_bilinear(Ctx *ctx, Pattern &P, const Prepared &R, const extf
     }
     if (rc == -1) return 0; // no instantiation: generic path
     if (rc) return rc;
+    if (int rcr = const_release(ctx)) return rcr;
     *fast = true;
     return 0;
 }
@@ -1357,11 +1432,11 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
     *fast = false;
     if (!ctx->fast_enabled) return 0;
     const OpDev &op = R.op;
-    if (d->ntest != 1 || d->nargs != 0 || d->test_op[0] != EXTFEM_OP_ID || op.nout != 1 || op.nq > TP_NQMAX) return 0;
+    if (d->ntest != 1 || d->nargs != 0 || d->test_op[0] != EXTFEM_OP_ID || op.nout != 1 || op.nq > TP_NQMAX || d->entities != EXTFEM_ON_CELLS) return 0;
     const int b = d->test_block[0];
     if (!P.square || b >= (int)P.colspaces.size() || P.poswidth != 1 || !P.coupling[(size_t)b * P.rowspaces.size() + b]) return 0;
     Space &S = *ctx->spaces[P.rowspaces[b]];
-    if (S.ncomp != 1 || S.nscalar > 10) return 0;
+    if (S.ncomp != 1 || S.nscalar > 10 || S.fetype == EXTFEM_FE_TABULATED) return 0;
     Mesh &M = *R.mesh;
     const int dim = op.dim, ns = S.nscalar;
     if (int rc = build_template_plan(ctx, P, b, ns)) return rc;
@@ -1372,6 +1447,7 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
     ref_basis(S.order, dim, Q, v, g);
     for (int q = 0; q < op.nq; ++q)
         for (int kl = 0; kl < ns; ++kl) phi[(size_t)kl * TP_NQMAX + q] = v[(size_t)q * ns + kl];
+    if (int rca = const_acquire(ctx)) return rca;
     EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_phi, phi.data(), phi.size() * 8, 0, cudaMemcpyHostToDevice, ctx->stream));
     if (int rc = ensure(ctx, ctx->fq, (size_t)T.Lg.Npad * op.nq * 8)) return rc;
     double *bblk = P.b.as<double>() + P.rowoff[b];
@@ -1419,7 +1495,99 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
     }
     EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
     EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (int rcr = const_release(ctx)) return rcr;
     *fast = true;
+    return 0;
+}
+
+// ---- ON_BFACES (entities.cuh): face-local kernels + owner-computes scatter into the cell pattern ---------------------
+static int scatter_faces_matrix(Ctx *ctx, Pattern &P, const Prepared &R)
+{
+    DevBuf err;
+    if (int rc = ensure(ctx, err, 4)) return rc;
+    EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(err.p, 0, 4, ctx->stream));
+    for (size_t ic = 0; ic < R.colblocks.size(); ++ic) {
+        const int cb = R.colblocks[ic];
+        Space &Sc = *ctx->spaces[P.colspaces[cb]]->bf;
+        FaceScatterArgs A;
+        memset(&A, 0, sizeof(A));
+        A.ncols = Sc.ndofs; A.colbase = P.coloff[cb];
+        A.adjptr = Sc.adjptr.as<long long>(); A.adjface = Sc.adjcell.as<int>(); A.adjloc = Sc.adjloc.as<unsigned char>();
+        A.collocoff = R.collocoff[ic];
+        A.nrb = 0;
+        for (size_t ir = 0; ir < R.testblocks.size(); ++ir) {
+            const int rb = R.testblocks[ir];
+            if (!P.coupling[(size_t)cb * P.rowspaces.size() + rb]) continue;   // block not in the pattern
+            Space &Sr = *ctx->spaces[P.rowspaces[rb]]->bf;
+            A.rowfacedofs[A.nrb] = Sr.celldofs.as<int>(); A.rownd[A.nrb] = Sr.nd; A.rowoff[A.nrb] = P.rowoff[rb];
+            A.rowlocoff[A.nrb] = R.testlocoff[ir];
+            ++A.nrb;
+        }
+        A.NRop = R.op.NR; A.NCop = R.op.NC; A.loc = ctx->loc.as<double>();
+        A.colptr = P.colptr.as<long long>(); A.rowval = P.rowval.as<int>(); A.nzval = P.nzval.as<double>(); A.error = err.as<int>();
+        face_scatter_matrix_kernel<<<nblocks(A.ncols, 256), 256, 0, ctx->stream>>>(A);
+        LAUNCHED(ctx);
+    }
+    int herr = 0;
+    EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(&herr, err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (herr) return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "ON_BFACES: a boundary-face entry is not part of the matrix pattern (BFaceDofs inconsistent with CellDofs?)");
+    return 0;
+}
+
+static int scatter_faces_vector(Ctx *ctx, Pattern &P, const Prepared &R)
+{
+    for (size_t ir = 0; ir < R.testblocks.size(); ++ir) {
+        const int rb = R.testblocks[ir];
+        Space &Sr = *ctx->spaces[P.rowspaces[rb]]->bf;
+        FaceScatterVecArgs A;
+        A.nrows = Sr.ndofs; A.rowbase = P.rowoff[rb];
+        A.adjptr = Sr.adjptr.as<long long>(); A.adjface = Sr.adjcell.as<int>(); A.adjloc = Sr.adjloc.as<unsigned char>();
+        A.rowlocoff = R.testlocoff[ir]; A.NRop = R.op.NR; A.bloc = ctx->bloc.as<double>(); A.b = P.b.as<double>();
+        face_scatter_vector_kernel<<<nblocks(A.nrows, 256), 256, 0, ctx->stream>>>(A);
+        LAUNCHED(ctx);
+    }
+    EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+static int assemble_bfaces(Ctx *ctx, Pattern &P, const Prepared &R, const extfem_opdesc *d, int kind, int accumulate)
+{
+    const OpDev &op = R.op;
+    if (d->transposed_copy != 0 || d->lump != 0)
+        return fail(ctx, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "ON_BFACES: transposed_copy / lump are not built");
+    if (kind == KIND_LINEAR && d->nargs > 0 && d->kernel_id != EXTFEM_BLK_STANDARD)
+        return fail(ctx, EXTFEM_ERR_UNREGISTERED_KERNEL, "LinearOperator with args supports only the standard kernel");
+    const int tdim = R.mesh->tdim;
+    EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (kind == KIND_BILINEAR) {
+        if (int rc = ensure(ctx, ctx->loc, (size_t)op.ncells * op.NR * op.NC * 8)) return rc;
+        if (!accumulate) EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(P.nzval.p, 0, (size_t)P.nnz * 8, ctx->stream));
+        const long long n = op.ncells * op.NR * op.NC;
+        int rcd = dispatch_dim(ctx, op.dim, [&](auto dimc) {
+            constexpr int DIM = decltype(dimc)::value;
+            face_bilinear_kernel<DIM><<<nblocks(n, 256), 256, 0, ctx->stream>>>(op, tdim, ctx->loc.as<double>());
+        });
+        if (rcd) return rcd;
+        LAUNCHED(ctx);
+        EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+        EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (int rc = scatter_faces_matrix(ctx, P, R)) return rc;
+    } else {
+        if (int rc = ensure(ctx, ctx->bloc, (size_t)op.ncells * op.NR * 8)) return rc;
+        if (!accumulate) EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(P.b.p, 0, (size_t)P.nrows * 8, ctx->stream));
+        const long long n = op.ncells * op.NR;
+        int rcd = dispatch_dim(ctx, op.dim, [&](auto dimc) {
+            constexpr int DIM = decltype(dimc)::value;
+            face_linear_kernel<DIM><<<nblocks(n, 256), 256, 0, ctx->stream>>>(op, tdim, ctx->bloc.as<double>());
+        });
+        if (rcd) return rcd;
+        LAUNCHED(ctx);
+        EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+        EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (int rc = scatter_faces_vector(ctx, P, R)) return rc;
+    }
+    EXTFEM_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     return 0;
 }
 
@@ -1472,6 +1640,7 @@ int extfem_ctx_destroy(extfem_ctx *ctx)
     C->patterns.clear(); C->spaces.clear(); C->meshes.clear();
     g_const_tmpl_owner[C->device % EXTFEM_MAXDEV] = nullptr;   // plans of this context may have owned the constant banks
     g_planemask_owner[C->device % EXTFEM_MAXDEV] = nullptr;
+    if (g_const_last_ctx[C->device % EXTFEM_MAXDEV] == C) g_const_last_ctx[C->device % EXTFEM_MAXDEV] = nullptr;
     if (C->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(C->dist.comm);
     cudaStream_t s = C->stream;
     delete C;
@@ -1490,10 +1659,13 @@ int extfem_kernel_id(const char *name)
     static const struct { const char *n; int id; } tab[] = {
         {"standard", EXTFEM_BLK_STANDARD}, {"dcr", EXTFEM_BLK_DCR}, {"stokes", EXTFEM_BLK_STOKES},
         {"linnse7", EXTFEM_BLK_LINNSE7}, {"hooke_grad", EXTFEM_BLK_HOOKE_GRAD}, {"hooke_voigt", EXTFEM_BLK_HOOKE_VOIGT},
-        {"convect_args", EXTFEM_BLK_CONVECT_ARGS},
+        {"convect_args", EXTFEM_BLK_CONVECT_ARGS}, {"robin108", EXTFEM_BLK_ROBIN108},
         {"constant_one", EXTFEM_LIN_CONSTANT_ONE}, {"constant_params", EXTFEM_LIN_CONSTANT_PARAMS}, {"xy", EXTFEM_LIN_XY},
-        {"sincos301", EXTFEM_LIN_SINCOS301}, {"tabulated", EXTFEM_LIN_TABULATED},
-        {"nse2d", EXTFEM_NL_NSE2D}, {"nl_linnse7", EXTFEM_NL_LINNSE7}, {"neohooke3d", EXTFEM_NL_NEOHOOKE3D}, {"rcd", EXTFEM_NL_RCD}};
+        {"sincos301", EXTFEM_LIN_SINCOS301}, {"tabulated", EXTFEM_LIN_TABULATED}, {"exp2x", EXTFEM_LIN_EXP2X}, {"step105", EXTFEM_LIN_STEP105},
+        {"nse2d", EXTFEM_NL_NSE2D}, {"nl_linnse7", EXTFEM_NL_LINNSE7}, {"neohooke3d", EXTFEM_NL_NEOHOOKE3D}, {"rcd", EXTFEM_NL_RCD},
+        {"nlpoisson105", EXTFEM_NL_NLPOISSON105}, {"stvenant230", EXTFEM_NL_STVENANT230},
+        {"ii_standard", EXTFEM_II_STANDARD}, {"l2norm", EXTFEM_II_L2NORM}, {"l2diff_tabulated", EXTFEM_II_L2DIFF_TABULATED},
+        {"l2err_sincos301", EXTFEM_II_L2ERR_SINCOS301}, {"l2err_exp108", EXTFEM_II_L2ERR_EXP108}};
     if (name)
         for (auto &t : tab) if (!strcmp(t.n, name)) return t.id;
     set_error(nullptr, EXTFEM_ERR_UNREGISTERED_KERNEL, std::string("kernel '") + (name ? name : "(null)") + "' is not registered");
@@ -1563,9 +1735,9 @@ int extfem_mesh_set(extfem_ctx *ctx, int dim, int64_t ncells, int64_t nnodes, co
         return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_mesh_set: bad argument");
     if (ncells >= (1ll << 31) || nnodes >= (1ll << 31)) return fail(C, EXTFEM_ERR_CAPACITY, "mesh too large for 32-bit device indices");
     auto M = std::make_unique<Mesh>();
-    M->dim = dim; M->ncells = ncells; M->nnodes = nnodes;
+    M->dim = dim; M->tdim = dim; M->ncells = ncells; M->nnodes = nnodes;
     if (int rc = upload(C, M->coords, coords, (size_t)nnodes * dim * 8)) return rc;
-    if (int rc = upload_indices(C, M->cellnodes, cellnodes, index_bytes, ncells * (dim + 1))) return rc;
+    if (int rc = upload_indices(C, M->cellnodes, cellnodes, index_bytes, ncells * (dim + 1), nnodes, "cellnodes")) return rc;
     if (cellregions) { if (int rc = upload(C, M->regions, cellregions, (size_t)ncells * 4)) return rc; }
     else {
         std::vector<int> ones((size_t)ncells, 1);
@@ -1596,8 +1768,43 @@ int extfem_mesh_update_coords(extfem_ctx *ctx, int mesh, const double *coords, c
         launch_cell_volumes(C->stream, M.dim, M.ncells, M.coords.as<double>(), M.cellnodes.as<int>(), M.vol.as<double>());
         LAUNCHED(C);
     }
-    M.geo_valid = false;
     ++M.vol_version;
+    if (M.bf && !M.bf_vol_given) {
+        face_volumes_kernel<<<nblocks(M.bf->ncells, 256), 256, 0, C->stream>>>(M.dim, M.bf->ncells, M.coords.as<double>(), M.bf->cellnodes.as<int>(),
+                                                                              M.bf->vol.as<double>());
+        LAUNCHED(C);
+    }
+    return EXTFEM_OK;
+}
+
+int extfem_mesh_set_bfaces(extfem_ctx *ctx, int mesh, int64_t nbfaces, const void *bfacenodes, int index_bytes, const int32_t *bfaceregions,
+                           const double *bfacevolumes)
+{
+    CTX_GUARD(ctx);
+    if (mesh < 0 || mesh >= (int)C->meshes.size() || nbfaces <= 0 || !bfacenodes || (index_bytes != 4 && index_bytes != 8))
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_mesh_set_bfaces: bad argument");
+    Mesh &M = *C->meshes[mesh];
+    auto B = std::make_unique<Mesh>();
+    B->dim = M.dim; B->tdim = M.dim - 1; B->ncells = nbfaces; B->nnodes = M.nnodes; B->parent = &M;
+    if (int rc = upload_indices(C, B->cellnodes, bfacenodes, index_bytes, nbfaces * M.dim, M.nnodes, "bfacenodes")) return rc;
+    if (bfaceregions) { if (int rc = upload(C, B->regions, bfaceregions, (size_t)nbfaces * 4)) return rc; }
+    else {
+        std::vector<int> ones((size_t)nbfaces, 1);
+        if (int rc = upload(C, B->regions, ones.data(), (size_t)nbfaces * 4)) return rc;
+        EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    }
+    if (int rc = ensure(C, B->vol, (size_t)nbfaces * 8)) return rc;
+    M.bf_vol_given = bfacevolumes != nullptr;
+    if (bfacevolumes) { EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(B->vol.p, bfacevolumes, (size_t)nbfaces * 8, cudaMemcpyDefault, C->stream)); }
+    else {
+        face_volumes_kernel<<<nblocks(nbfaces, 256), 256, 0, C->stream>>>(M.dim, nbfaces, M.coords.as<double>(), B->cellnodes.as<int>(), B->vol.as<double>());
+        LAUNCHED(C);
+    }
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    M.bf = std::move(B);
+    // spaces created before the boundary faces keep their BFaceDofs handle only if the face count is unchanged
+    for (auto &S : C->spaces)
+        if (S && S->mesh == mesh && S->bf && S->bf->celldofs.bytes != (size_t)nbfaces * S->bf->nd * 4) S->bf.reset();
     return EXTFEM_OK;
 }
 
@@ -1608,27 +1815,72 @@ int extfem_space_set(extfem_ctx *ctx, int mesh, int fetype, int ncomp, const voi
     if (mesh < 0 || mesh >= (int)C->meshes.size() || !celldofs || !space_out || ncomp < 1 || (index_bytes != 4 && index_bytes != 8))
         return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_space_set: bad argument");
     Mesh &M = *C->meshes[mesh];
-    int order = fetype == EXTFEM_FE_H1P1 ? 1 : (fetype == EXTFEM_FE_H1P2 ? 2 : -1);
+    int order = fetype == EXTFEM_FE_H1P1 ? 1 : (fetype == EXTFEM_FE_H1P2 ? 2 : (fetype == EXTFEM_FE_TABULATED ? 0 : -1));
     if (order < 0)
-        return fail(C, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "fetype " + std::to_string(fetype) + " is not supported (H1P1, H1P2 / H1Pk order<=2)");
-    int ns = nscalar_of(order, M.dim);
-    if (ndofs4cell != ns * ncomp)
+        return fail(C, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "fetype " + std::to_string(fetype) +
+                                                        " is not supported (H1P1, H1P2 / H1Pk order<=2, or EXTFEM_FE_TABULATED + extfem_space_set_tables)");
+    int ns = fetype == EXTFEM_FE_TABULATED ? ndofs4cell / ncomp : nscalar_of(order, M.dim);
+    if (ndofs4cell != ns * ncomp || ns < 1)
         return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "ndofs4cell does not match the element (expected " + std::to_string(ns * ncomp) + ")");
     if (ndofs4cell > 255) return fail(C, EXTFEM_ERR_CAPACITY, "ndofs4cell > 255");
     if (ndofs >= (1ll << 31)) return fail(C, EXTFEM_ERR_CAPACITY, "too many dofs for 32-bit device indices");
     auto S = std::make_unique<Space>();
     S->mesh = mesh; S->fetype = fetype; S->order = order; S->ncomp = ncomp; S->nscalar = ns; S->nd = ndofs4cell; S->ndofs = ndofs;
-    if (int rc = upload_indices(C, S->celldofs, celldofs, index_bytes, M.ncells * ndofs4cell)) return rc;
+    if (int rc = upload_indices(C, S->celldofs, celldofs, index_bytes, M.ncells * ndofs4cell, ndofs, "celldofs")) return rc;
     if (int rc = build_adjacency(C, *S, M.ncells)) return rc;
+    S->id = (int)C->spaces.size();
     C->spaces.push_back(std::move(S));
     *space_out = (int)C->spaces.size() - 1;
     return EXTFEM_OK;
 }
 
-int extfem_space_set_tables(extfem_ctx *ctx, int, int, int, const double *, const double *)
+int extfem_space_set_tables(extfem_ctx *ctx, int space, int order, int nscalar, const double *coeffs, int nscalar_bface, const double *bface_coeffs)
 {
     CTX_GUARD(ctx);
-    return fail(C, EXTFEM_ERR_UNSUPPORTED_ELEMENT, "host-tabulated elements are not implemented yet");
+    if (space < 0 || space >= (int)C->spaces.size() || !coeffs) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_space_set_tables: bad argument");
+    Space &S = *C->spaces[space];
+    if (S.fetype != EXTFEM_FE_TABULATED) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_space_set_tables: the space is not EXTFEM_FE_TABULATED");
+    if (order < 0 || order > 8) return fail(C, EXTFEM_ERR_CAPACITY, "extfem_space_set_tables: polynomial order must be 0..8");
+    if (nscalar != S.nscalar) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_space_set_tables: nscalar does not match ndofs4cell / ncomp");
+    Mesh &M = *C->meshes[S.mesh];
+    S.order = order;
+    S.poly.assign(coeffs, coeffs + (size_t)nscalar * nmonomials(order, M.dim));
+    S.tabkey = 2 * S.id;
+    S.poly_ready = true;
+    S.nscalar_bf = 0; S.bpoly.clear();
+    if (bface_coeffs && nscalar_bface > 0) {
+        S.nscalar_bf = nscalar_bface;
+        S.bpoly.assign(bface_coeffs, bface_coeffs + (size_t)nscalar_bface * nmonomials(order, M.dim - 1));
+    }
+    if (S.bf) {   // BFaceDofs attached before the basis
+        S.bf->order = order; S.bf->poly = S.bpoly; S.bf->poly_ready = !S.bpoly.empty() && S.bf->nscalar == S.nscalar_bf;
+    }
+    // cached tables of an earlier basis of this space are stale
+    for (auto it = C->tables.begin(); it != C->tables.end();)
+        if (it->first.space == 2 * S.id || it->first.space == 2 * S.id + 1) it = C->tables.erase(it); else ++it;
+    return EXTFEM_OK;
+}
+
+int extfem_space_set_bfacedofs(extfem_ctx *ctx, int space, const void *bfacedofs, int index_bytes, int ndofs4bface)
+{
+    CTX_GUARD(ctx);
+    if (space < 0 || space >= (int)C->spaces.size() || !bfacedofs || (index_bytes != 4 && index_bytes != 8) || ndofs4bface < 1)
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_space_set_bfacedofs: bad argument");
+    Space &S = *C->spaces[space];
+    Mesh &M = *C->meshes[S.mesh];
+    if (!M.bf) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_space_set_bfacedofs: call extfem_mesh_set_bfaces on the grid first");
+    const bool tab = S.fetype == EXTFEM_FE_TABULATED;
+    const int ns = tab ? ndofs4bface / S.ncomp : nscalar_of(S.order, M.dim - 1);
+    if (ndofs4bface != ns * S.ncomp || ndofs4bface > 255)
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "ndofs4bface does not match the element (expected " + std::to_string(ns * S.ncomp) + ")");
+    auto B = std::make_unique<Space>();
+    B->id = S.id; B->mesh = S.mesh; B->fetype = S.fetype; B->order = S.order; B->ncomp = S.ncomp; B->nscalar = ns; B->nd = ndofs4bface; B->ndofs = S.ndofs;
+    B->tabkey = tab ? 2 * S.id + 1 : -1;
+    if (tab) { B->poly = S.bpoly; B->poly_ready = S.poly_ready && !S.bpoly.empty() && S.nscalar_bf == ns; }
+    if (int rc = upload_indices(C, B->celldofs, bfacedofs, index_bytes, M.bf->ncells * ndofs4bface, S.ndofs, "bfacedofs")) return rc;
+    if (int rc = build_adjacency(C, *B, M.bf->ncells)) return rc;
+    S.bf = std::move(B);
+    return EXTFEM_OK;
 }
 
 int extfem_pattern_build(extfem_ctx *ctx, int nrow, const int *rowspaces, int ncol, const int *colspaces,
@@ -1697,7 +1949,7 @@ int extfem_pattern_build(extfem_ctx *ctx, int nrow, const int *rowspaces, int nc
         DevBuf dmax;
         if (int rc = ensure(C, dmax, 8)) return rc;
         size_t tb = 0;
-        cub::DeviceReduce::Max(nullptr, tb, collen.as<long long>(), dmax.as<long long>(), (int)(P.ncols), C->stream);
+        cub::DeviceReduce::Max(nullptr, tb, collen.as<long long>(), dmax.as<long long>(), (long long)P.ncols, C->stream);
         if (int rc = ensure(C, tmp, tb)) return rc;
         EXTFEM_CUDA_CHECK(C, cub::DeviceReduce::Max(tmp.p, tb, collen.as<long long>(), dmax.as<long long>(), (long long)P.ncols, C->stream));
         LAUNCHED(C);
@@ -1799,6 +2051,11 @@ int extfem_assemble_bilinear(extfem_ctx *ctx, int pattern, const extfem_opdesc *
     GET_PATTERN(pattern);
     Prepared R;
     if (int rc = prepare(C, P, d, KIND_BILINEAR, d && d->nargs > 0 ? sol : nullptr, R)) return rc;
+    if (R.entities == EXTFEM_ON_BFACES) {
+        if (int rc = assemble_bfaces(C, P, R, d, KIND_BILINEAR, accumulate)) return rc;
+        if (nzval_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(nzval_out, P.nzval.p, (size_t)P.nnz * 8, cudaMemcpyDefault, C->stream));
+        return finish_timing(C, nzval_out != nullptr);
+    }
     EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[0], C->stream));
     bool fast = false;
     if (int rc = try_fast_bilinear(C, P, R, d, accumulate, &fast)) return rc;
@@ -1829,6 +2086,11 @@ int extfem_assemble_linear(extfem_ctx *ctx, int pattern, const extfem_opdesc *d,
     Prepared R;
     if (int rc = prepare(C, P, d, KIND_LINEAR, d && d->nargs > 0 ? sol : nullptr, R)) return rc;
     const OpDev &op = R.op;
+    if (R.entities == EXTFEM_ON_BFACES) {
+        if (int rc = assemble_bfaces(C, P, R, d, KIND_LINEAR, accumulate)) return rc;
+        if (b_out) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b_out, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+        return finish_timing(C, b_out != nullptr);
+    }
     EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[0], C->stream));
     bool fast = false;
     if (int rc = try_fast_linear(C, P, R, d, accumulate, &fast)) return rc;
@@ -1969,6 +2231,83 @@ int extfem_quadrature_points(extfem_ctx *ctx, int pattern, const extfem_opdesc *
     return EXTFEM_OK;
 }
 
+int extfem_integrate(extfem_ctx *ctx, int pattern, const extfem_opdesc *d, const double *sol, int resultdim, int piecewise, double *out)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (!out || !sol) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_integrate: sol / out is NULL");
+    Prepared R;
+    if (int rc = prepare(C, P, d, KIND_INTEGRATE, sol, R)) return rc;
+    OpDev &op = R.op;
+    if (resultdim <= 0) resultdim = op.nin;     // :resultdim == 0: length of the arguments (item_integrator.jl:188-192)
+    if (resultdim > MAXOP) return fail(C, EXTFEM_ERR_CAPACITY, "resultdim larger than MAXOP");
+    if ((d->kernel_id == EXTFEM_II_L2ERR_SINCOS301 || d->kernel_id == EXTFEM_II_L2ERR_EXP108) && (resultdim != 1 || op.nin < 1))
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "exact-error kernels integrate one scalar argument");
+    if (d->kernel_id == EXTFEM_II_L2DIFF_TABULATED) {
+        if (!d->tabulated || resultdim > op.nin) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "l2diff_tabulated needs reference values [ncells][nq][resultdim]");
+        if (int rc = upload(C, C->tab, d->tabulated, (size_t)op.ncells * op.nq * resultdim * 8)) return rc;
+        op.tabulated = C->tab.as<double>();
+    }
+    DevBuf &vals = C->loc;
+    if (int rc = ensure(C, vals, (size_t)op.ncells * resultdim * 8)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[0], C->stream));
+    int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
+        constexpr int DIM = decltype(dimc)::value;
+        item_integrate_kernel<DIM><<<nblocks(op.ncells, 128), 128, 0, C->stream>>>(op, resultdim, vals.as<double>());
+    });
+    if (rcd) return rcd;
+    LAUNCHED(C);
+    EXTFEM_CUDA_CHECK(C, cudaGetLastError());
+    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[1], C->stream));
+    if (piecewise) {
+        EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(out, vals.p, (size_t)op.ncells * resultdim * 8, cudaMemcpyDefault, C->stream));
+    } else {
+        DevBuf part;
+        if (int rc = ensure(C, part, (size_t)(RED_BLOCKS + 1) * resultdim * 8)) return rc;
+        ii_reduce_partial_kernel<<<RED_BLOCKS, 256, 0, C->stream>>>(op.ncells, resultdim, vals.as<double>(), part.as<double>());
+        ii_reduce_final_kernel<<<1, 256, 0, C->stream>>>(RED_BLOCKS, resultdim, part.as<double>(), part.as<double>() + (size_t)RED_BLOCKS * resultdim);
+        LAUNCHED(C); LAUNCHED(C);
+        EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(out, part.as<double>() + (size_t)RED_BLOCKS * resultdim, (size_t)resultdim * 8, cudaMemcpyDefault, C->stream));
+        EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));   // part is freed on return
+    }
+    EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev[2], C->stream));
+    return finish_timing(C, true);
+}
+
+int extfem_values_zero(extfem_ctx *ctx, int pattern, int zero_matrix, int zero_rhs)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (zero_matrix) EXTFEM_CUDA_CHECK(C, cudaMemsetAsync(P.nzval.p, 0, (size_t)P.nnz * 8, C->stream));
+    if (zero_rhs) EXTFEM_CUDA_CHECK(C, cudaMemsetAsync(P.b.p, 0, (size_t)P.nrows * 8, C->stream));
+    return EXTFEM_OK;
+}
+
+int extfem_apply_values(extfem_ctx *ctx, int64_t ndofs, const int64_t *dofs, const double *values, double *sol, int64_t nsol)
+{
+    CTX_GUARD(ctx);
+    if (ndofs == 0) return EXTFEM_OK;
+    if (!dofs || !sol || nsol <= 0) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_apply_values: bad argument");
+    cudaPointerAttributes at;
+    const bool dev = cudaPointerGetAttributes(&at, sol) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    DevBuf dd, dv, ds, err;
+    if (int rc = upload(C, dd, dofs, (size_t)ndofs * 8)) return rc;
+    if (values) if (int rc = upload(C, dv, values, (size_t)ndofs * 8)) return rc;
+    double *target = sol;
+    if (!dev) { if (int rc = upload(C, ds, sol, (size_t)nsol * 8)) return rc; target = ds.as<double>(); }
+    if (int rc = ensure(C, err, 4)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaMemsetAsync(err.p, 0, 4, C->stream));
+    apply_values_kernel<<<nblocks(ndofs, 256), 256, 0, C->stream>>>(ndofs, dd.as<long long>(), values ? dv.as<double>() : nullptr, target, nsol, err.as<int>());
+    LAUNCHED(C);
+    if (!dev) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(sol, target, (size_t)nsol * 8, cudaMemcpyDeviceToHost, C->stream));
+    int herr = 0;
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(&herr, err.p, 4, cudaMemcpyDeviceToHost, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    if (herr) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_apply_values: dof out of range");
+    return EXTFEM_OK;
+}
+
 int extfem_values_get(extfem_ctx *ctx, int pattern, double *nzval, double *b)
 {
     CTX_GUARD(ctx);
@@ -2012,9 +2351,11 @@ int extfem_apply_penalties(extfem_ctx *ctx, int pattern, int64_t ndofs, const in
     DevBuf err;
     if (int rc = ensure(C, err, 4)) return rc;
     EXTFEM_CUDA_CHECK(C, cudaMemsetAsync(err.p, 0, 4, C->stream));
+    // sharded system: the diagonal lives on the owning rank only (additive form), b stays consistent
+    const double *owned = (C->dist.ready && C->dist.world > 1 && P.iface.ready) ? (const double *)P.iface.weight : nullptr;
     penalties_kernel<<<nblocks(ndofs, 256), 256, 0, C->stream>>>(ndofs, dd.as<long long>(), values ? dv.as<double>() : nullptr, penalty,
                                                                 P.colptr.as<long long>(), P.rowval.as<int>(), P.nzval.as<double>(),
-                                                                P.b.as<double>(), P.nrows, err.as<int>());
+                                                                P.b.as<double>(), P.nrows, owned, err.as<int>());
     LAUNCHED(C);
     int herr = 0;
     EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(&herr, err.p, 4, cudaMemcpyDeviceToHost, C->stream));

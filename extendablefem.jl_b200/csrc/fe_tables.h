@@ -91,7 +91,9 @@ inline QuadRule quadrature_rule(int dim, int order)
         for (double v : p) Q.x.push_back(v);
         Q.w.push_back(wt);
     };
-    if (order <= 1) {
+    if (dim == 0) {
+        Q.w.push_back(1.0);   // a vertex (boundary "face" of a 1D grid): one point of weight 1, no coordinates
+    } else if (order <= 1) {
         if (dim == 1) push({0.5}, 1.0);
         if (dim == 2) push({1.0 / 3, 1.0 / 3}, 1.0);
         if (dim == 3) push({0.25, 0.25, 0.25}, 1.0);
@@ -128,6 +130,7 @@ inline QuadRule quadrature_rule(int dim, int order)
 
 inline int nscalar_of(int order, int dim)
 {
+    if (dim == 0) return 1;
     if (order == 1) return dim + 1;
     if (order == 2) return dim == 1 ? 3 : (dim == 2 ? 6 : 10);
     return -1;
@@ -142,6 +145,7 @@ inline void ref_basis(int order, int dim, const QuadRule &Q, std::vector<double>
     int ns = nscalar_of(order, dim), nq = Q.nq;
     vals.assign((size_t)nq * ns, 0.0);
     grads.assign((size_t)nq * ns * dim, 0.0);
+    if (dim == 0) { for (int q = 0; q < nq; ++q) vals[q] = 1.0; return; }
     for (int q = 0; q < nq; ++q) {
         double lam[4], dlam[4][3];
         double s = 0;
@@ -169,6 +173,57 @@ inline void ref_basis(int order, int dim, const QuadRule &Q, std::vector<double>
                 v[i] = 4 * lam[a] * lam[b];
                 for (int d = 0; d < dim; ++d) g[i * dim + d] = 4 * (lam[a] * dlam[b][d] + lam[b] * dlam[a][d]);
             }
+        }
+    }
+}
+
+// ---- host-supplied polynomial reference bases (EXTFEM_FE_TABULATED, extfem_space_set_tables) ----------------------
+// monomials x^i y^j z^k, i+j+k <= order, enumerated `for k: for j: for i` (i fastest)
+inline int nmonomials(int order, int dim)
+{
+    int n = 1;
+    for (int d = 1; d <= dim; ++d) n = n * (order + d) / d;
+    return n;
+}
+
+inline void poly_basis(int order, int dim, int ns, const std::vector<double> &coeffs, const QuadRule &Q, std::vector<double> &vals,
+                       std::vector<double> &grads)
+{
+    const int nq = Q.nq, nm = nmonomials(order, dim);
+    vals.assign((size_t)nq * ns, 0.0);
+    grads.assign((size_t)nq * ns * std::max(dim, 1), 0.0);
+    if (dim == 0) { for (int q = 0; q < nq; ++q) for (int s = 0; s < ns; ++s) vals[(size_t)q * ns + s] = coeffs[s]; return; }
+    std::vector<double> mv(nm), mg((size_t)nm * dim);
+    for (int q = 0; q < nq; ++q) {
+        double x[3] = {0, 0, 0};
+        for (int d = 0; d < dim; ++d) x[d] = Q.x[(size_t)q * dim + d];
+        int m = 0;
+        const int K = dim >= 3 ? order : 0;
+        for (int k = 0; k <= K; ++k) {
+            const int J = dim >= 2 ? order - k : 0;
+            for (int j = 0; j <= J; ++j)
+                for (int i = 0; i <= order - k - j; ++i, ++m) {
+                    const int e[3] = {i, j, k};
+                    double v = 1.0;
+                    for (int d = 0; d < dim; ++d) v *= std::pow(x[d], e[d]);
+                    mv[m] = v;
+                    for (int d = 0; d < dim; ++d) {
+                        double g = e[d];
+                        if (e[d] > 0)
+                            for (int d2 = 0; d2 < dim; ++d2) g *= std::pow(x[d2], d2 == d ? e[d2] - 1 : e[d2]);
+                        mg[(size_t)m * dim + d] = e[d] > 0 ? g : 0.0;
+                    }
+                }
+        }
+        for (int s = 0; s < ns; ++s) {
+            double v = 0.0, g[3] = {0, 0, 0};
+            for (int mm = 0; mm < nm; ++mm) {
+                const double c = coeffs[(size_t)s * nm + mm];
+                v += c * mv[mm];
+                for (int d = 0; d < dim; ++d) g[d] += c * mg[(size_t)mm * dim + d];
+            }
+            vals[(size_t)q * ns + s] = v;
+            for (int d = 0; d < dim; ++d) grads[((size_t)q * ns + s) * dim + d] = g[d];
         }
     }
 }

@@ -123,6 +123,9 @@ __device__ __forceinline__ void bl_apply(int id, int dim, const double *in, cons
             r[c] = s;
         }
         break;
+    case EXTFEM_BLK_ROBIN108:   // Example108:48-51: evaluated per basis function like every bilinear kernel (:891)
+        for (int d = 0; d < nout; ++d) r[d] = p[0] - in[d];
+        break;
     }
 }
 
@@ -135,13 +138,15 @@ __device__ __forceinline__ void lin_apply(int id, const double *x, const double 
     case EXTFEM_LIN_XY: r[0] = x[0] * x[1]; break;
     case EXTFEM_LIN_SINCOS301: r[0] = p[0] * (1.7 * 1.7 + 3.9 * 3.9) * sin(1.7 * x[0]) * cos(3.9 * x[1]); break;
     case EXTFEM_LIN_TABULATED: for (int d = 0; d < nout; ++d) r[d] = tab[d]; break;
+    case EXTFEM_LIN_EXP2X: r[0] = exp(2.0 * x[0]); break;
+    case EXTFEM_LIN_STEP105: r[0] = x[0] < 0.5 ? -1.0 : 1.0; break;
     }
 }
 
 // ---- registry: nonlinear kernels with analytic Jacobians ----------------------------------
 // value[nout], jac[nout][nin] (row-major, written densely)
 __device__ __forceinline__ void nl_apply(int id, int dim, const double *in, const double *p, double *val, double *J,
-                                         int nin, int nout)
+                                         int nin, int nout, int region = 1)
 {
     for (int i = 0; i < nin * nout; ++i) J[i] = 0.0;
     switch (id) {
@@ -225,6 +230,28 @@ __device__ __forceinline__ void nl_apply(int id, int dim, const double *in, cons
         J[0 * nin + 0] = in[1] + 1.0;
         J[0 * nin + 1] = in[0];
         for (int d = 0; d < dim; ++d) { val[1 + d] = in[1 + d]; J[(1 + d) * nin + 1 + d] = 1.0; }
+    } break;
+    case EXTFEM_NL_NLPOISSON105: {
+        const double ep = exp(in[0]), em = exp(-in[0]);
+        val[0] = ep - em;
+        J[0] = ep + em;
+        for (int d = 0; d < dim; ++d) { val[1 + d] = p[0] * in[1 + d]; J[(1 + d) * nin + 1 + d] = p[0]; }
+    } break;
+    case EXTFEM_NL_STVENANT230: {
+        // Green-Lagrange strain (Voigt) minus thermal strain, isotropic Hooke; material by cell region
+        const int R = (int)p[0], m = region >= 1 && region <= R ? region - 1 : 0;
+        const double la = p[1 + m], mu = p[1 + R + m], eT = p[1 + 2 * R + m];
+        const double g1 = in[0], g2 = in[1], g3 = in[2], g4 = in[3];
+        const double e1 = g1 + 0.5 * (g1 * g1 + g3 * g3) - eT, e2 = g4 + 0.5 * (g2 * g2 + g4 * g4) - eT;
+        const double e3 = g2 + g3 + g1 * g2 + g3 * g4;
+        const double a = la * (e1 + e2) + 2.0 * mu * e1, b = la * (e1 + e2) + 2.0 * mu * e2, c = 2.0 * mu * e3;
+        val[0] = a; val[1] = c; val[2] = c; val[3] = b;
+        const double d1[4] = {1.0 + g1, 0.0, g3, 0.0}, d2[4] = {0.0, g2, 0.0, 1.0 + g4}, d3[4] = {g2, 1.0 + g1, 1.0 + g4, g3};
+        for (int j = 0; j < 4; ++j) {
+            J[0 * 4 + j] = (la + 2.0 * mu) * d1[j] + la * d2[j];
+            J[3 * 4 + j] = la * d1[j] + (la + 2.0 * mu) * d2[j];
+            J[1 * 4 + j] = J[2 * 4 + j] = 2.0 * mu * d3[j];
+        }
     } break;
     }
 }
@@ -485,7 +512,7 @@ local_nonlinear_kernel(const __grid_constant__ OpDev op, double *__restrict__ lo
         double u[MAXOP], val[MAXOP];
         eval_args<DIM>(op, c0 + s, q, G, u);
         double *J = jq + (size_t)t * JS;
-        nl_apply(op.kernel_id, DIM, u, op.params, val, J, nin, nout);
+        nl_apply(op.kernel_id, DIM, u, op.params, val, J, nin, nout, op.cellregions[c0 + s]);
         double sc = op.factor * op.qw[q] * G.vol;
         for (int k = 0; k < nout; ++k) {
             double sum = 0.0;
@@ -630,7 +657,7 @@ local_nonlinear_kernel2(const __grid_constant__ OpDev op, double *__restrict__ l
             }
         }
         double *J = jq_of(s) + (size_t)q * JS;
-        nl_apply(op.kernel_id, DIM, u, op.params, val, J, nin, nout);
+        nl_apply(op.kernel_id, DIM, u, op.params, val, J, nin, nout, op.cellregions[c0 + s]);
         const double sc = op.factor * op.qw[q] * G.vol;
         for (int k = 0; k < nout; ++k) {
             double sum = 0.0;
@@ -799,7 +826,7 @@ local_nonlinear_kernel3(const __grid_constant__ OpDev op, const __grid_constant_
             double ur[MAXOP], val[MAXOP];
             for (int d = 0; d < nin; ++d) ur[d] = uq[q * nin + d];
             double *J = Jq + (size_t)q * JS;
-            nl_apply(op.kernel_id, DIM, ur, op.params, val, J, nin, nout);
+            nl_apply(op.kernel_id, DIM, ur, op.params, val, J, nin, nout, op.cellregions[cell]);
             const double w = op.qw[q], sc = op.factor * w * G.vol;
             for (int k = 0; k < nout; ++k) {
                 double sum = 0.0;

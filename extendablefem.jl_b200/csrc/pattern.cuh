@@ -192,11 +192,13 @@ __global__ void fill_i64_kernel(long long *p, long long n, long long v)
     if (i < n) p[i] = v;
 }
 
-__global__ void convert_index_kernel(const void *__restrict__ in, int index_bytes, long long n, int *__restrict__ out)
+__global__ void convert_index_kernel(const void *__restrict__ in, int index_bytes, long long n, long long nmax, int *__restrict__ out,
+                                     int *__restrict__ err)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     long long v = index_bytes == 8 ? reinterpret_cast<const long long *>(in)[i] : reinterpret_cast<const int *>(in)[i];
+    if (v < 1 || v > nmax) { atomicExch(err, 1); v = 1; }
     out[i] = (int)(v - 1);
 }
 

@@ -129,7 +129,7 @@ __device__ __forceinline__ long long find_in_column(const long long *colptr, con
 
 __global__ void penalties_kernel(long long n, const long long *__restrict__ dofs, const double *__restrict__ values, double penalty,
                                  const long long *__restrict__ colptr, const int *__restrict__ rowval, double *__restrict__ nzval,
-                                 double *__restrict__ b, long long nrows, int *err)
+                                 double *__restrict__ b, long long nrows, const double *__restrict__ owned, int *err)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -137,7 +137,7 @@ __global__ void penalties_kernel(long long n, const long long *__restrict__ dofs
     if (d < 0 || d >= nrows) { atomicExch(err, 1); return; }
     long long p = find_in_column(colptr, rowval, d, (int)d);
     if (p < 0) { atomicExch(err, 1); return; }
-    nzval[p] = penalty;
+    nzval[p] = (owned && owned[d] == 0.0) ? 0.0 : penalty;
     b[d] = penalty * (values ? values[i] : 0.0);
 }
 
@@ -217,7 +217,8 @@ static inline int jacobi_cg(cudaStream_t st, long long n, long long nnz, const l
 {
     (void)nnz;
     if (W.n_alloc < n) {
-        for (auto &v : W.vec) { if (v) cudaFree(v); if (cudaMalloc(&v, n * 8)) return -1; }
+        W.n_alloc = 0;
+        for (auto &v : W.vec) { if (v) { cudaFree(v); v = nullptr; } if (cudaMalloc(&v, n * 8)) { v = nullptr; return -1; } }
         if (!W.partial && cudaMalloc(&W.partial, RED_BLOCKS * 8)) return -1;
         if (!W.scalars && cudaMalloc(&W.scalars, 8 * 8)) return -1;
         W.n_alloc = n;

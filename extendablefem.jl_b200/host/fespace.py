@@ -19,9 +19,11 @@ from .grids import ExtendableGrid
 # element ids shared with include/extfem_cuda.h
 EXTFEM_FE_H1P1 = 1
 EXTFEM_FE_H1P2 = 2
+EXTFEM_FE_TABULATED = 100
 
 __all__ = ["FESpace", "H1P1", "H1P2", "H1Pk", "FEVector", "FEVectorBlock", "FEMatrix",
-           "EXTFEM_FE_H1P1", "EXTFEM_FE_H1P2", "interpolate"]
+           "EXTFEM_FE_H1P1", "EXTFEM_FE_H1P2", "EXTFEM_FE_TABULATED", "interpolate", "monomial_exponents",
+           "lagrange_nodes_p3", "nodal_basis_coefficients"]
 
 
 @dataclass(frozen=True)
@@ -33,7 +35,8 @@ class FEType:
 
     @property
     def fe_id(self) -> int:
-        return {1: EXTFEM_FE_H1P1, 2: EXTFEM_FE_H1P2}[self.order]
+        # order 3 is not built into the engine: it goes in as a host-supplied polynomial basis (extfem_space_set_tables)
+        return {1: EXTFEM_FE_H1P1, 2: EXTFEM_FE_H1P2, 3: EXTFEM_FE_TABULATED}[self.order]
 
 
 def H1P1(ncomponents: int, edim: int | None = None) -> FEType:
@@ -45,10 +48,48 @@ def H1P2(ncomponents: int, edim: int) -> FEType:
 
 
 def H1Pk(ncomponents: int, edim: int, order: int) -> FEType:
-    if order not in (1, 2):
-        raise NotImplementedError(
-            "H1Pk with order > 2 is not supported by the B200 engine (EXTFEM_ERR_UNSUPPORTED_ELEMENT)")
+    """``H1Pk{ncomponents, edim, order}``.  Orders 1 and 2 are built into the engine; order 3 (README.md:50, Example201:66;
+    edim <= 2 here) is handed to it as a polynomial reference basis."""
+    if order not in (1, 2, 3) or (order == 3 and edim > 2):
+        raise NotImplementedError("H1Pk: orders 1-2 (any dimension) and order 3 (edim <= 2) are provided")
     return FEType("H1Pk", ncomponents, edim, order)
+
+
+def monomial_exponents(order: int, dim: int):
+    """Monomial enumeration of extfem_space_set_tables: x^i y^j z^k, ``for k: for j: for i`` (i fastest)."""
+    out = []
+    for k in range(order + 1 if dim >= 3 else 1):
+        for j in range(order - k + 1 if dim >= 2 else 1):
+            for i in range(order - k - j + 1):
+                out.append((i, j, k)[:max(dim, 1)])
+    return out
+
+
+def lagrange_nodes_p3(dim: int) -> np.ndarray:
+    """Reference Lagrange points of the cubic element in local dof order: vertices, two per edge (a,b) at 1/3 and 2/3 from a
+    to b (local edge order of the grid), then the cell centre (2D)."""
+    if dim == 0:
+        return np.zeros((1, 0))
+    verts = np.concatenate([np.zeros((1, dim)), np.eye(dim)])
+    edges = {1: [(0, 1)], 2: [(0, 1), (1, 2), (2, 0)]}[dim]
+    pts = [v for v in verts]
+    for a, b in edges:
+        pts.append(verts[a] + (verts[b] - verts[a]) / 3.0)
+        pts.append(verts[a] + 2.0 * (verts[b] - verts[a]) / 3.0)
+    if dim == 2:
+        pts.append(verts.mean(axis=0))
+    return np.array(pts)
+
+
+def nodal_basis_coefficients(nodes: np.ndarray, order: int) -> np.ndarray:
+    """coeffs[j][m]: basis_j = sum_m coeffs[j][m] * monomial_m with basis_j(node_i) = delta_ij."""
+    dim = nodes.shape[1]
+    if dim == 0:
+        return np.ones((1, 1))
+    ex = monomial_exponents(order, dim)
+    V = np.stack([np.prod(nodes ** np.array(e)[None, :], axis=1) for e in ex], axis=1)   # [node][monomial]
+    assert V.shape[0] == V.shape[1], V.shape
+    return np.ascontiguousarray(np.linalg.inv(V).T)
 
 
 class FESpace:
@@ -59,7 +100,12 @@ class FESpace:
         self.xgrid = xgrid
         g = xgrid
         nn = g.nnodes
-        if fetype.order == 1:
+        self.ref_coeffs = self.ref_coeffs_bface = None
+        if fetype.order == 3:
+            scalar, bscalar, nscalar = self._p3_dofs(g)
+            self.ref_coeffs = nodal_basis_coefficients(lagrange_nodes_p3(g.dim), 3)
+            self.ref_coeffs_bface = nodal_basis_coefficients(lagrange_nodes_p3(g.dim - 1), 3)
+        elif fetype.order == 1:
             scalar = g.cellnodes.astype(np.int64)
             nscalar = nn
             bscalar = g.bfacenodes.astype(np.int64)
@@ -82,6 +128,37 @@ class FESpace:
         self.bfacedofs = np.concatenate([bscalar + c * nscalar for c in range(nc)], axis=1).astype(np.int32)
 
     @staticmethod
+    def _p3_dofs(g):
+        """Cubic Lagrange dofs: nodes, then two per edge -- the first one next to the edge's LOWER global node --, then one
+        per cell (2D).  A cell lists the two dofs of a local edge (a,b) in the order (next to a, next to b), so the reference
+        basis is the same in every cell and the edge orientation lives in the dof map."""
+        nn = g.nnodes
+        cn = g.cellnodes.astype(np.int64)
+        bn = g.bfacenodes.astype(np.int64)
+        if g.dim == 1:
+            first = nn + 2 * np.arange(g.ncells, dtype=np.int64) + 1
+            flip = cn[:, 0] > cn[:, 1]
+            e1 = np.where(flip, first + 1, first); e2 = np.where(flip, first, first + 1)
+            return np.concatenate([cn, e1[:, None], e2[:, None]], axis=1), bn, nn + 2 * g.ncells
+        edgenodes, celledges = g.edges()
+        ne = edgenodes.shape[0]
+        loc = {2: [(0, 1), (1, 2), (2, 0)]}[g.dim]
+        cols = [cn]
+        for le, (a, b) in enumerate(loc):
+            first = nn + 2 * (celledges[:, le].astype(np.int64) - 1) + 1
+            flip = cn[:, a] > cn[:, b]
+            cols += [np.where(flip, first + 1, first)[:, None], np.where(flip, first, first + 1)[:, None]]
+        cols.append((nn + 2 * ne + np.arange(1, g.ncells + 1, dtype=np.int64))[:, None])
+        # boundary faces (edges): nodes, then the edge's two dofs in the face's own direction
+        en = edgenodes.astype(np.int64)
+        keys = en[:, 0] * (nn + 1) + en[:, 1]
+        lo, hi = np.minimum(bn[:, 0], bn[:, 1]), np.maximum(bn[:, 0], bn[:, 1])
+        first = nn + 2 * np.searchsorted(keys, lo * (nn + 1) + hi) + 1
+        flip = bn[:, 0] > bn[:, 1]
+        bcols = [bn, np.where(flip, first + 1, first)[:, None], np.where(flip, first, first + 1)[:, None]]
+        return np.concatenate(cols, axis=1), np.concatenate(bcols, axis=1), nn + 2 * ne + g.ncells
+
+    @staticmethod
     def _bface_scalar_dofs(g, edgenodes, nn):
         bn = g.bfacenodes.astype(np.int64)
         if g.dim == 1:
@@ -102,6 +179,14 @@ class FESpace:
     def dof_coordinates(self) -> np.ndarray:
         """Coordinates of the scalar Lagrange points (nodes, then edge midpoints)."""
         g = self.xgrid
+        if self.fetype.order == 3:
+            # every dof is a Lagrange point: read it off the cells (reference points in local dof order)
+            ref = lagrange_nodes_p3(g.dim)
+            lam = np.concatenate([1.0 - ref.sum(axis=1, keepdims=True), ref], axis=1)            # [nloc, dim+1]
+            x = np.einsum("lv,cvd->cld", lam, g.coords[g.cellnodes.astype(np.int64) - 1])         # [ncells, nloc, dim]
+            out = np.zeros((self.coffset, g.dim))
+            out[self.celldofs[:, :ref.shape[0]].astype(np.int64) - 1] = x
+            return out
         if self.fetype.order == 1:
             return g.coords
         if g.dim == 1:

@@ -216,15 +216,32 @@ def grid_unitsquare(scale=(1.0, 1.0), shift=(0.0, 0.0)) -> ExtendableGrid:
 
 
 def grid_unitcube() -> ExtendableGrid:
-    """``grid_unitcube(Tetrahedron3D)``: 8 nodes, 6 tets (Kuhn split)."""
-    return simplexgrid([0.0, 1.0], [0.0, 1.0], [0.0, 1.0])
+    """``grid_unitcube(Tetrahedron3D)``: 8 nodes, 6 tets around the diagonal (0,0,0)-(1,1,1), in ExtendableGrids' node and
+    cell order as recalled (the package is not in /root/reference): with it and the refinement rule below, Example301's
+    acceptance bound ``L2error <= 8.56e-5`` (examples/Example301_PoissonProblem.jl:89-105) is met at 8.548e-5, whereas other
+    interior-diagonal choices give 1.16e-4 (tests/test_oracle_golden.py).  Boundary regions 1:z=0 2:y=0 3:x=1 4:y=1 5:x=0 6:z=1."""
+    coords = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], dtype=np.float64)
+    cn = np.array([[1, 2, 3, 7], [1, 3, 4, 7], [1, 5, 6, 7], [1, 8, 5, 7], [1, 6, 2, 7], [1, 4, 8, 7]], dtype=np.int32)
+    seen = {}
+    for c in cn:
+        for f in TET_FACES:
+            seen.setdefault(tuple(sorted(c[f])), []).append(c[f])
+    bf = np.array([v[0] for v in seen.values() if len(v) == 1], dtype=np.int32)
+    mid = coords[bf - 1].mean(axis=1)
+    reg = np.zeros(bf.shape[0], np.int32)
+    for r, (ax, val) in enumerate(((2, 0.0), (1, 0.0), (0, 1.0), (1, 1.0), (0, 0.0), (2, 1.0)), start=1):
+        reg[np.isclose(mid[:, ax], val)] = r
+    return ExtendableGrid(coords, cn, np.ones(6, np.int32), bf, reg)
 
 
 # ---------------------------------------------------------------------------
 # uniform (red) refinement
 # ---------------------------------------------------------------------------
 def uniform_refine(g: ExtendableGrid, nrefs: int = 1) -> ExtendableGrid:
-    """Red refinement: every simplex is split into 2^dim children (3D: Bey's rule)."""
+    """Red refinement: every simplex is split into 2^dim children.  3D: ExtendableGrids' rule as recalled -- with the edge
+    midpoints numbered 5..10 in local-edge order the children are (1 5 6 7) (2 5 9 8) (3 10 6 8) (4 10 9 7) (10 5 8 9)
+    (5 10 7 9) (5 10 8 6) (10 5 7 6), i.e. the inner octahedron is cut along the midpoints of the local edges 12 and 34
+    (see grid_unitcube for the evidence)."""
     for _ in range(nrefs):
         g = _refine_once(g)
     return g
@@ -262,8 +279,8 @@ def _refine_once(g: ExtendableGrid) -> ExtendableGrid:
         v0, v1, v2, v3 = cn.T
         m01, m02, m03, m12, m13, m23 = m.T
         kids = [np.stack(k, axis=1) for k in (
-            (v0, m01, m02, m03), (m01, v1, m12, m13), (m02, m12, v2, m23), (m03, m13, m23, v3),
-            (m01, m02, m03, m13), (m01, m02, m12, m13), (m02, m03, m13, m23), (m02, m12, m13, m23))]
+            (v0, m01, m02, m03), (v1, m01, m13, m12), (v2, m23, m02, m12), (v3, m23, m13, m03),
+            (m23, m01, m12, m13), (m01, m23, m03, m13), (m01, m23, m12, m02), (m23, m01, m03, m02))]
         nk = 8
     newcn = np.empty((nk * g.ncells, dim + 1), np.int64)
     for k, kid in enumerate(kids):

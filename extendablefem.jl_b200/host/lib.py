@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libextfem_cuda.so")
 
 MAXARGS = 4
 OP_ID, OP_GRAD, OP_DIV, OP_SYMGRAD_VOIGT = 0, 1, 2, 3
+ON_CELLS, ON_BFACES = 0, 1
+FE_TABULATED = 100
 
 EXPORTS = [
     "extfem_ctx_create", "extfem_ctx_destroy", "extfem_last_error", "extfem_kernel_id", "extfem_synchronize", "extfem_set_option",
@@ -24,6 +26,7 @@ EXPORTS = [
     "extfem_quadrature_points", "extfem_values_get", "extfem_values_set", "extfem_device_ptrs",
     "extfem_apply_penalties", "extfem_residual", "extfem_spmv", "extfem_cg", "extfem_plan_stats", "extfem_plan_jit_status",
     "extfem_dist_unique_id", "extfem_dist_init", "extfem_dist_set_interfaces", "extfem_dist_sum_rhs", "extfem_dist_spmv", "extfem_dist_cg",
+    "extfem_mesh_set_bfaces", "extfem_space_set_bfacedofs", "extfem_integrate", "extfem_values_zero", "extfem_apply_values",
 ]
 
 
@@ -44,6 +47,7 @@ class OpDesc(C.Structure):
         ("nregions", C.c_int32), ("regions", C.c_void_p),
         ("transposed_copy", C.c_int32), ("lump", C.c_int32), ("coupling", C.c_void_p),
         ("nq_custom", C.c_int32), ("qweights", C.c_void_p), ("qpoints", C.c_void_p), ("tabulated", C.c_void_p),
+        ("entities", C.c_int32),
     ]
 
 
@@ -124,6 +128,14 @@ class Engine:
                                              cellnodes.dtype.itemsize, _p(reg), _p(vol), C.byref(out)))
         return out.value
 
+    def mesh_set_bfaces(self, mesh: int, bfacenodes, bfaceregions=None, bfacevolumes=None):
+        """xgrid[BFaceNodes], xgrid[BFaceRegions], xgrid[BFaceVolumes]"""
+        bn = np.ascontiguousarray(bfacenodes)
+        assert bn.dtype in (np.int32, np.int64)
+        reg = None if bfaceregions is None else np.ascontiguousarray(bfaceregions, dtype=np.int32)
+        vol = None if bfacevolumes is None else np.ascontiguousarray(bfacevolumes, dtype=np.float64)
+        self._check(self.lib.extfem_mesh_set_bfaces(self.ctx, mesh, C.c_int64(bn.shape[0]), _p(bn), bn.dtype.itemsize, _p(reg), _p(vol)))
+
     def mesh_update_coords(self, mesh: int, coords, cellvolumes=None):
         self._check(self.lib.extfem_mesh_update_coords(self.ctx, mesh, _p(coords), _p(cellvolumes)))
 
@@ -134,6 +146,27 @@ class Engine:
         self._check(self.lib.extfem_space_set(self.ctx, mesh, fetype, ncomp, _p(celldofs), celldofs.dtype.itemsize,
                                               celldofs.shape[1], C.c_int64(ndofs), C.byref(out)))
         return out.value
+
+    def space_set_tables(self, space: int, order: int, coeffs, bface_coeffs=None):
+        """EXTFEM_FE_TABULATED: polynomial reference basis coeffs[nscalar][nmono] (+ its restriction to a boundary face)."""
+        cf = np.ascontiguousarray(coeffs, dtype=np.float64)
+        bf = None if bface_coeffs is None else np.ascontiguousarray(bface_coeffs, dtype=np.float64)
+        self._check(self.lib.extfem_space_set_tables(self.ctx, space, int(order), cf.shape[0], _p(cf),
+                                                     0 if bf is None else bf.shape[0], _p(bf)))
+
+    def space_set_bfacedofs(self, space: int, bfacedofs):
+        """FES[BFaceDofs]"""
+        bd = np.ascontiguousarray(bfacedofs)
+        assert bd.dtype in (np.int32, np.int64)
+        self._check(self.lib.extfem_space_set_bfacedofs(self.ctx, space, _p(bd), bd.dtype.itemsize, bd.shape[1]))
+
+    def fespace_set(self, mesh: int, FES) -> int:
+        """Uploads a host FESpace: cell dof map, boundary-face dof map (when the grid's bfaces were set) and, for elements
+        that are not built in, the polynomial reference basis."""
+        sp = self.space_set(mesh, FES.fetype.fe_id, FES.fetype.ncomponents, FES.celldofs, FES.ndofs)
+        if FES.fetype.fe_id == FE_TABULATED:
+            self.space_set_tables(sp, FES.fetype.order, FES.ref_coeffs, FES.ref_coeffs_bface)
+        return sp
 
     def pattern_build(self, rowspaces, colspaces=None, block_coupling=None) -> int:
         colspaces = rowspaces if colspaces is None else colspaces
@@ -159,7 +192,7 @@ class Engine:
     # ---- operators -------------------------------------------------------------------------------
     def make_opdesc(self, test, ansatz=(), args=(), kernel_id=1, params=(), factor=1.0, time=0.0, quadorder=-1,
                     bonus_quadorder=0, regions=(), transposed_copy=0, lump=0, coupling=None, offdiag=1.0,
-                    qweights=None, qpoints=None, tabulated=None):
+                    qweights=None, qpoints=None, tabulated=None, entities=ON_CELLS):
         """test/ansatz/args: sequences of (block, op)."""
         d = OpDesc()
         keep = []
@@ -191,6 +224,7 @@ class Engine:
                 tabulated = np.ascontiguousarray(tabulated, dtype=np.float64)
             keep.append(tabulated)
             d.tabulated = _p(tabulated)
+        d.entities = int(entities)
         d._keep = keep
         return d
 
@@ -215,7 +249,27 @@ class Engine:
         self._check(self.lib.extfem_quadrature_points(self.ctx, pattern, C.byref(desc), int(is_linear), C.byref(C.c_int()), _p(xq)))
         return xq
 
+    def integrate(self, pattern, desc, sol, resultdim=0, piecewise=True, nitems=None):
+        """ItemIntegrator ``evaluate``: [nitems, resultdim] (piecewise) or [resultdim]."""
+        sol = np.ascontiguousarray(sol, dtype=np.float64)
+        if resultdim <= 0:
+            raise ValueError("resultdim must be given (the length of the arguments when the reference says 0)")
+        out = np.empty((nitems, resultdim)) if piecewise else np.empty(resultdim)
+        self._check(self.lib.extfem_integrate(self.ctx, pattern, C.byref(desc), _p(sol), int(resultdim), int(piecewise), _p(out)))
+        return out
+
     # ---- device-resident system ----------------------------------------------------------------
+    def values_zero(self, pattern, matrix=True, rhs=True):
+        """fill!(nzval, 0) / fill!(b, 0) at the start of assemble_system! (src/solvers.jl:130-135)"""
+        self._check(self.lib.extfem_values_zero(self.ctx, pattern, int(matrix), int(rhs)))
+
+    def apply_values(self, dofs, values, sol):
+        """sol[dofs] = values (the assemble_sol leg of apply_penalties!); sol is modified in place"""
+        dofs = np.ascontiguousarray(dofs, dtype=np.int64)
+        vals = None if values is None else np.ascontiguousarray(values, dtype=np.float64)
+        assert isinstance(sol, np.ndarray) and sol.dtype == np.float64 and sol.flags.c_contiguous
+        self._check(self.lib.extfem_apply_values(self.ctx, C.c_int64(dofs.size), _p(dofs), _p(vals), _p(sol), C.c_int64(sol.size)))
+
     def values_get(self, pattern, want_nzval=True, want_b=True, nzval_out=None, b_out=None):
         """Device-resident values; ``*_out`` (numpy array / pinned torch tensor / device pointer) receive them in place."""
         nrows, ncols, nnz = self.pattern_dims(pattern)

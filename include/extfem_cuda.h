@@ -30,8 +30,9 @@
  *    the reference's value-dependent pattern (entries exactly 0.0 are never inserted,
  *    bilinear_operator.jl:925) is always a subset of it.
  *  - a context is not re-entrant; calls on one context are serialised by the caller.  Several contexts may live in one
- *    process (one per device, or several on one device used one after the other); contexts on the SAME device must not
- *    run concurrently (they share the device's __constant__ tables).
+ *    process (one per device, or several on one device): contexts on the SAME device share the device's __constant__
+ *    tables; the library orders a context's upload behind the other context's last kernel that read them (event wait), so
+ *    they may be used alternately without extfem_synchronize, but not from two host threads at once.
  *  - there is no CPU fallback: without a CUDA device extfem_ctx_create fails.
  */
 #ifndef EXTFEM_CUDA_H
@@ -58,6 +59,8 @@ enum {
 
 /* ---- finite elements / function operators ----------------------------------------------- */
 enum { EXTFEM_FE_H1P1 = 1, EXTFEM_FE_H1P2 = 2, EXTFEM_FE_TABULATED = 100 };
+/* assembly entities (:entities kwarg, bilinear_operator.jl:61, 707-714): cells or boundary faces */
+enum { EXTFEM_ON_CELLS = 0, EXTFEM_ON_BFACES = 1 };
 /* function operators (ExtendableFEMBase: Identity, Gradient, Divergence, SymmetricGradient) */
 enum { EXTFEM_OP_ID = 0, EXTFEM_OP_GRAD = 1, EXTFEM_OP_DIV = 2, EXTFEM_OP_SYMGRAD_VOIGT = 3 };
 
@@ -69,21 +72,35 @@ enum { /* BilinearOperator kernels: result = C(x, args) * input */
     EXTFEM_BLK_LINNSE7 = 4,      /* "linnse7"       test/test_nonlinear_operator.jl:18-28; params mu, alpha      */
     EXTFEM_BLK_HOOKE_GRAD = 5,   /* "hooke_grad"    isotropic Hooke on grad(u); params mu, lambda                */
     EXTFEM_BLK_HOOKE_VOIGT = 6,  /* "hooke_voigt"   Example312:55 sigma = C*epsV(u); params C row-major          */
-    EXTFEM_BLK_CONVECT_ARGS = 7  /* "convect_args"  (args . grad) u, kernel with args (bilinear_operator.jl:536)  */
+    EXTFEM_BLK_CONVECT_ARGS = 7, /* "convect_args"  (args . grad) u, kernel with args (bilinear_operator.jl:536)  */
+    EXTFEM_BLK_ROBIN108 = 8      /* "robin108"      Example108:48-51 result = params[0] - input (used ON_BFACES)     */
 };
 enum { /* LinearOperator kernels f(x) */
     EXTFEM_LIN_CONSTANT_ONE = 1,    /* "constant_one"    constant_one_kernel (linear_operator.jl:159)  */
     EXTFEM_LIN_CONSTANT_PARAMS = 2, /* "constant_params" result .= params (Example330:44, Example312:58) */
     EXTFEM_LIN_XY = 3,              /* "xy"              README.md:37-40 / Example201:32-35              */
     EXTFEM_LIN_SINCOS301 = 4,       /* "sincos301"       Example301:33-35; params mu                     */
-    EXTFEM_LIN_TABULATED = 5        /* "tabulated"       any Julia closure, evaluated by the host at the
+    EXTFEM_LIN_TABULATED = 5,       /* "tabulated"       any Julia closure, evaluated by the host at the
                                                          quadrature points (extfem_quadrature_points)    */
+    EXTFEM_LIN_EXP2X = 6,           /* "exp2x"           Example108:31-34  f = exp(2 x1)                 */
+    EXTFEM_LIN_STEP105 = 7          /* "step105"         Example105:35-38  f = x1 < 0.5 ? -1 : 1         */
 };
 enum { /* NonlinearOperator kernels with analytic Jacobians */
     EXTFEM_NL_NSE2D = 1,       /* "nse2d"       Example250:59-74; params mu          */
     EXTFEM_NL_LINNSE7 = 2,     /* "nl_linnse7"  test/test_nonlinear_operator.jl:18-28 */
     EXTFEM_NL_NEOHOOKE3D = 3,  /* "neohooke3d"  Example330:49-57 (DW); params mu, lambda */
-    EXTFEM_NL_RCD = 4          /* "rcd"         Example108:40-45                        */
+    EXTFEM_NL_RCD = 4,         /* "rcd"         Example108:40-45                        */
+    EXTFEM_NL_NLPOISSON105 = 5,/* "nlpoisson105" Example105:45-50 [exp(u)-exp(-u), eps grad u]; params eps */
+    EXTFEM_NL_STVENANT230 = 6  /* "stvenant230" Example230:39-72 (2D, [grad(u)]); params R, lambda[R], mu[R], epsT[R]
+                                                 indexed by the cell region                  */
+};
+enum { /* ItemIntegrator kernels (item_integrator.jl:26-28, 71-81 and the examples' exact_error! closures) */
+    EXTFEM_II_STANDARD = 1,         /* "ii_standard"      result = input (ItemIntegrator(oa_args), item_integrator.jl:78-81) */
+    EXTFEM_II_L2NORM = 2,           /* "l2norm"           l2norm_kernel: result = input.^2 (item_integrator.jl:26-28)        */
+    EXTFEM_II_L2DIFF_TABULATED = 3, /* "l2diff_tabulated" (ref - input).^2 with ref evaluated by the host at the quadrature
+                                                          points (any exact_error! closure)                               */
+    EXTFEM_II_L2ERR_SINCOS301 = 4,  /* "l2err_sincos301"  Example301:62-67 (sin(1.7x)cos(3.9y) - u)^2                      */
+    EXTFEM_II_L2ERR_EXP108 = 5      /* "l2err_exp108"     Example108:86-90 (exp(x) - u)^2                                  */
 };
 
 #define EXTFEM_MAXARGS 4 /* (unknown, operator) pairs per role */
@@ -112,7 +129,8 @@ typedef struct {
     int32_t nq_custom;
     const double *qweights;    /* [nq]                                                 */
     const double *qpoints;     /* [nq][dim]                                            */
-    const double *tabulated;   /* EXTFEM_LIN_TABULATED: [ncells][nq][oplen]            */
+    const double *tabulated;   /* EXTFEM_LIN_TABULATED / EXTFEM_II_L2DIFF_TABULATED: [nitems][nq][oplen] */
+    int32_t entities;          /* :entities, EXTFEM_ON_CELLS (0) or EXTFEM_ON_BFACES   */
 } extfem_opdesc;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -146,16 +164,29 @@ int extfem_event_elapsed_ms(extfem_ctx *ctx, int slot_start, int slot_stop, doub
 int extfem_mesh_set(extfem_ctx *ctx, int dim, int64_t ncells, int64_t nnodes, const double *coords,
                     const void *cellnodes, int index_bytes, const int32_t *cellregions /* NULL: all 1 */,
                     const double *cellvolumes /* NULL: computed */, int *mesh_out);
+/* boundary faces of the grid: xgrid[BFaceNodes], xgrid[BFaceRegions], xgrid[BFaceVolumes] (read by the ON_BFACES branch of
+ * build_assembler!, bilinear_operator.jl:693-714).  bfacenodes[dim, nbfaces] column-major, 1-based. */
+int extfem_mesh_set_bfaces(extfem_ctx *ctx, int mesh, int64_t nbfaces, const void *bfacenodes, int index_bytes,
+                           const int32_t *bfaceregions /* NULL: all 1 */, const double *bfacevolumes /* NULL: computed */);
 /* new node coordinates for an existing mesh (moving meshes; refreshes the geometry cache) */
 int extfem_mesh_update_coords(extfem_ctx *ctx, int mesh, const double *coords, const double *cellvolumes);
 
 /* ---- FESpace: FES[CellDofs] via get_dofmap (src/helper_functions.jl:561-567) ------------- */
 int extfem_space_set(extfem_ctx *ctx, int mesh, int fetype, int ncomp, const void *celldofs, int index_bytes,
                      int ndofs4cell, int64_t ndofs, int *space_out);
-/* EXTFEM_FE_TABULATED: reference basis supplied by the host (any affine H1 Lagrange-type element):
- * the engine evaluates vals/grads through callbacks-free tables given per quadrature rule.     */
-int extfem_space_set_tables(extfem_ctx *ctx, int space, int nq, int nscalar, const double *refvals /*[nq][nscalar]*/,
-                            const double *refgrads /*[nq][nscalar][dim]*/);
+/* EXTFEM_FE_TABULATED (any affine H1-conforming scalar-Lagrange-type element, e.g. H1Pk order 3 of README.md:50 /
+ * Example201:66): the host supplies the scalar reference basis as POLYNOMIALS in the reference coordinates, so the engine can
+ * evaluate values and gradients at the points of whatever quadrature rule an operator asks for.  coeffs[nscalar][nmono]
+ * (row-major), monomials x^i y^j z^k with i+j+k <= order enumerated by `for k: for j: for i` (i fastest; lower dimensions drop
+ * the outer loops): nmono = binomial(order + dim, dim).  extfem_space_set with fetype == EXTFEM_FE_TABULATED creates the space
+ * (nscalar = ndofs4cell / ncomp); it cannot be used before its basis is set.  bface_coeffs (may be NULL) is the basis of the
+ * restriction to a boundary face in the face's own reference coordinates, [nscalar_bface][binomial(order + dim-1, dim-1)].
+ * Cell-wise orientation-dependent elements keep ONE reference basis here: the host orders `celldofs` per cell accordingly. */
+int extfem_space_set_tables(extfem_ctx *ctx, int space, int order, int nscalar, const double *coeffs,
+                            int nscalar_bface, const double *bface_coeffs);
+/* FES[BFaceDofs] (read through get_dofmap for ON_BFACES, src/helper_functions.jl:561-567): bfacedofs[ndofs4bface, nbfaces],
+ * 1-based, same global numbering as celldofs; needs extfem_mesh_set_bfaces on the space's mesh.                        */
+int extfem_space_set_bfacedofs(extfem_ctx *ctx, int space, const void *bfacedofs, int index_bytes, int ndofs4bface);
 
 /* ---- FEMatrix pattern (replaces ExtendableSparse rawupdateindex!/flush!) ------------------
  * Block system with row blocks `rowspaces` and column blocks `colspaces`; block (r,c) is
@@ -188,20 +219,38 @@ int extfem_plan_jit_status(extfem_ctx *ctx, int pattern, int block);
 int extfem_quadrature_points(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, int is_linear, int *nq_out,
                              double *xq);
 
+/* ---- ItemIntegrator (src/common_operators/item_integrator.jl:191-249, evaluate :323-352): integrates
+ *      kernel(input_args(sol), qpinfo) over every cell.  `op` uses args_* (blocks index the pattern's column blocks), kernel_id
+ *      (EXTFEM_II_*), params, factor, quadorder ("auto" = max polynomial order of the arguments, :147-151), regions, tabulated.
+ *      piecewise != 0: out[resultdim, ncells] column-major (the matrix `evaluate` returns); else out[resultdim] (sum over cells). */
+int extfem_integrate(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, const double *sol, int resultdim, int piecewise,
+                     double *out);
+
 /* ---- device-resident system --------------------------------------------------------------- */
+/* fill!(A.entries.cscmatrix.nzval, 0) / fill!(b.entries, 0) at the start of assemble_system! (src/solvers.jl:130-135) */
+int extfem_values_zero(extfem_ctx *ctx, int pattern, int zero_matrix, int zero_rhs);
 int extfem_values_get(extfem_ctx *ctx, int pattern, double *nzval /*NULL ok*/, double *b /*NULL ok*/);
 int extfem_values_set(extfem_ctx *ctx, int pattern, const double *nzval /*NULL ok*/, const double *b /*NULL ok*/);
 /* raw device pointers (colptr int64 0-based, rowval int32 0-based, nzval, b) for zero-copy users */
 int extfem_device_ptrs(extfem_ctx *ctx, int pattern, void **colptr, void **rowval, void **nzval, void **b);
-/* apply_penalties! (homogeneousdata_operator.jl:186-201): A[d,d] = penalty, b[d] = penalty*value[d] */
+/* apply_penalties! (homogeneousdata_operator.jl:186-201): A[d,d] = penalty, b[d] = penalty*value[d].  On a sharded system
+ * (after extfem_dist_set_interfaces) every rank passes ALL its local boundary dofs, like the reference does per partition: the
+ * diagonal is written on the owning rank only (0 elsewhere, the additive sum is `penalty`) and b[d] = penalty*value[d] on every
+ * sharing rank (b stays consistent; call it after extfem_dist_sum_rhs).                                                */
 int extfem_apply_penalties(extfem_ctx *ctx, int pattern, int64_t ndofs, const int64_t *dofs /*1-based*/,
                            const double *values /*NULL: 0*/, double penalty);
+/* the assemble_sol leg of apply_penalties! (homogeneousdata_operator.jl:198-201, interpolateboundarydata_operator.jl:160-167):
+ * sol[dofs] = values (NULL: 0) on a caller vector (host or device pointer)                                              */
+int extfem_apply_values(extfem_ctx *ctx, int64_t ndofs, const int64_t *dofs /*1-based*/, const double *values, double *sol,
+                        int64_t nsol);
 /* compute_nonlinear_residual! (src/solvers.jl:38-43): res = b - A*sol */
 int extfem_residual(extfem_ctx *ctx, int pattern, const double *sol, double *res_out);
 /* y = A*x on the device-resident matrix */
 int extfem_spmv(extfem_ctx *ctx, int pattern, const double *x, double *y);
 /* Jacobi-preconditioned CG on the device-resident system (square patterns); b == NULL uses the
- * device-resident right-hand side.  x is in/out (initial guess).                              */
+ * device-resident right-hand side.  x is in/out (initial guess).  The matrix must be SYMMETRIC positive definite: the CSC
+ * arrays are traversed as CSR (A^T x); use extfem_spmv / extfem_residual (which build a true row-major view) for
+ * non-symmetric systems such as Newton matrices of convection terms.                           */
 int extfem_cg(extfem_ctx *ctx, int pattern, const double *b, double *x, double rtol, int maxit, int *iters,
               double *relres);
 

@@ -47,6 +47,8 @@ typedef struct {
     const int32_t *cellnodes;  /* [ncells][dim+1], 1-based    */
     const int32_t *cellregions;/* [ncells]                    */
     const double *cellvolumes; /* [ncells]                    */
+    int tdim;                  /* topological dimension of the items: dim (cells) or dim-1 (boundary faces:
+                                  xgrid[BFaceNodes/BFaceRegions/BFaceVolumes], bilinear_operator.jl:693-714) */
 } ora_mesh;
 
 /* one (FESpace, FunctionOperator) pair == one FEEvaluator of the reference */
@@ -74,6 +76,15 @@ typedef struct {               /* COO sink in the reference's insertion order */
     int64_t n, cap;
 } ora_coo;
 
+/* Test aid: when set, every TERM of every sum (basis evaluations, solution coefficients, kernel results, Jacobian entries) enters
+ * by its absolute value, so an assembly returns, entry by entry, the sum of |terms| behind that entry: the scale of a
+ * componentwise backward-error comparison |fl(sum t_i) - sum t_i| <= c * eps * sum |t_i| between two summation orders
+ * (tests/util.py: check_values_entrywise). */
+static int g_abs_accumulate = 0;
+void ora_set_abs_accumulate(int on) { g_abs_accumulate = on; }
+#define ORA_ACC(v) (g_abs_accumulate ? fabs(v) : (v))
+static void ora_abs_vec(double *v, int n) { if (g_abs_accumulate) for (int i = 0; i < n; ++i) v[i] = fabs(v[i]); }
+
 static int arg_ndofs(const ora_arg *a) { return a->ncomp * a->nscalar; }
 static int arg_oplen(const ora_arg *a, int dim)
 {
@@ -91,14 +102,15 @@ typedef struct { double x0[3]; double A[3][3]; double Ainv[3][3]; double det; } 
 
 static void update_trafo(ora_trafo *T, const ora_mesh *m, int64_t cell)
 {
-    int dim = m->dim;
-    const int32_t *cn = m->cellnodes + cell * (dim + 1);
+    int dim = m->dim, tdim = m->tdim;
+    const int32_t *cn = m->cellnodes + cell * (tdim + 1);
     const double *p0 = m->coords + (int64_t)(cn[0] - 1) * dim;
     for (int d = 0; d < dim; ++d) T->x0[d] = p0[d];
-    for (int r = 0; r < dim; ++r) {
+    for (int r = 0; r < tdim; ++r) {
         const double *pr = m->coords + (int64_t)(cn[r + 1] - 1) * dim;
         for (int d = 0; d < dim; ++d) T->A[d][r] = pr[d] - p0[d];
     }
+    if (tdim < dim) return; /* boundary faces: only the affine map is needed (Identity operators) */
     if (dim == 1) {
         T->det = T->A[0][0];
         T->Ainv[0][0] = 1.0 / T->A[0][0];
@@ -126,11 +138,11 @@ static void update_trafo(ora_trafo *T, const ora_mesh *m, int64_t cell)
     }
 }
 
-static void eval_trafo(double *x, const ora_trafo *T, const double *xref, int dim)
+static void eval_trafo(double *x, const ora_trafo *T, const double *xref, int dim, int tdim)
 {
     for (int d = 0; d < dim; ++d) {
         double s = T->x0[d];
-        for (int r = 0; r < dim; ++r) s += T->A[d][r] * xref[r];
+        for (int r = 0; r < tdim; ++r) s += T->A[d][r] * xref[r];
         x[d] = s;
     }
 }
@@ -138,7 +150,7 @@ static void eval_trafo(double *x, const ora_trafo *T, const double *xref, int di
 /* ---- update_basis!: cvals[d, j, qp] for one evaluator on one cell ----------------- */
 /* layout: cvals[(qp*ndofs + j)*oplen + d]  (Julia cvals[d,j,qp], column-major)        */
 static void update_basis(double *cvals, const ora_arg *a, const ora_trafo *T, int dim, int nq)
-{
+{   /* on boundary faces (tdim < dim) only Identity operators are evaluated (refgrads unused) */
     int ndofs = arg_ndofs(a), oplen = arg_oplen(a, dim), ns = a->nscalar;
     memset(cvals, 0, sizeof(double) * (size_t)nq * ndofs * oplen);
     for (int qp = 0; qp < nq; ++qp) {
@@ -174,6 +186,7 @@ static void update_basis(double *cvals, const ora_arg *a, const ora_trafo *T, in
             }
         }
     }
+    ora_abs_vec(cvals, nq * ndofs * oplen);
 }
 
 /* =====================================================================================
@@ -186,20 +199,32 @@ enum {
     ORA_BLK_LINNSE7 = 4,   /* test/test_nonlinear_operator.jl:18-28 ; params mu, alpha            */
     ORA_BLK_HOOKE_GRAD = 5,/* isotropic Hooke on grad(u): mu(G+G^T)+lambda tr(G) I ; params mu,lambda */
     ORA_BLK_HOOKE_VOIGT = 6,/* examples/Example312_PeriodicElasticity3D.jl:55 sigma = C*eps ; params C row-major */
-    ORA_BLK_CONVECT_ARGS = 7 /* with-args kernel: (beta=u_args . grad)u ; test kernel for :451-596 */
+    ORA_BLK_CONVECT_ARGS = 7,/* with-args kernel: (beta=u_args . grad)u ; test kernel for :451-596 */
+    ORA_BLK_ROBIN108 = 8     /* examples/Example108_RobinBoundaryCondition.jl:48-51 ; params g     */
 };
 enum {
     ORA_LIN_CONSTANT_ONE = 1, /* ExtendableFEMBase.constant_one_kernel (linear_operator.jl:159) */
     ORA_LIN_CONSTANT_PARAMS = 2, /* result .= params (Example330 apply_force!, Example312 linear_kernel!) */
     ORA_LIN_XY = 3,           /* README.md:37-40, Example201:32-35  f = x*y                      */
     ORA_LIN_SINCOS301 = 4,    /* examples/Example301_PoissonProblem.jl:33-35                     */
-    ORA_LIN_TABULATED = 5     /* values supplied per (cell, qp, component)                       */
+    ORA_LIN_TABULATED = 5,    /* values supplied per (cell, qp, component)                       */
+    ORA_LIN_EXP2X = 6,        /* examples/Example108_RobinBoundaryCondition.jl:31-34             */
+    ORA_LIN_STEP105 = 7       /* examples/Example105_NonlinearPoissonEquation.jl:35-38           */
 };
 enum {
     ORA_NL_NSE2D = 1,      /* examples/Example250_NSELidDrivenCavity.jl:59-74 ; params mu        */
     ORA_NL_LINNSE7 = 2,    /* test/test_nonlinear_operator.jl:18-28 ; params mu, alpha           */
     ORA_NL_NEOHOOKE3D = 3, /* examples/Example330_HyperElasticity.jl:49-57 (DW) ; params mu,lambda */
-    ORA_NL_RCD = 4         /* examples/Example108_RobinBoundaryCondition.jl:40-45 (any dim: u*du/dx1+u ; grad) */
+    ORA_NL_RCD = 4,        /* examples/Example108_RobinBoundaryCondition.jl:40-45 (any dim: u*du/dx1+u ; grad) */
+    ORA_NL_NLPOISSON105 = 5, /* examples/Example105_NonlinearPoissonEquation.jl:45-50 ; params eps */
+    ORA_NL_STVENANT230 = 6 /* examples/Example230_NonlinearElasticity.jl:39-72 ; params R, lambda[R], mu[R], epsT[R] */
+};
+enum {
+    ORA_II_STANDARD = 1,   /* ExtendableFEMBase.standard_kernel (item_integrator.jl:78-81)              */
+    ORA_II_L2NORM = 2,     /* l2norm_kernel (item_integrator.jl:26-28)                                  */
+    ORA_II_L2DIFF_TABULATED = 3, /* (ref - input)^2, ref supplied per (cell, qp, component)              */
+    ORA_II_L2ERR_SINCOS301 = 4,  /* examples/Example301_PoissonProblem.jl:37-40,62-67                    */
+    ORA_II_L2ERR_EXP108 = 5      /* examples/Example108_RobinBoundaryCondition.jl:35-38,86-90           */
 };
 
 static int bl_kernel(int id, int dim, double *r, const double *in, const double *args, const ora_qpinfo *qp, int oplen)
@@ -260,6 +285,9 @@ static int bl_kernel(int id, int dim, double *r, const double *in, const double 
         }
         return 0;
     }
+    case ORA_BLK_ROBIN108: /* result[1] = 2 - input[1] with g = params[0] */
+        for (int d = 0; d < oplen; ++d) r[d] = p[0] - in[d];
+        return 0;
     }
     return -1;
 }
@@ -275,6 +303,8 @@ static int lin_kernel(int id, double *r, const ora_qpinfo *qp, int oplen, const 
         r[0] = p[0] * (1.7 * 1.7 + 3.9 * 3.9) * sin(1.7 * qp->x[0]) * cos(3.9 * qp->x[1]);
         return 0;
     case ORA_LIN_TABULATED: for (int d = 0; d < oplen; ++d) r[d] = tab[d]; return 0;
+    case ORA_LIN_EXP2X: r[0] = exp(2 * qp->x[0]); return 0;
+    case ORA_LIN_STEP105: r[0] = qp->x[0] < 0.5 ? -1 : 1; return 0;
     }
     return -1;
 }
@@ -338,6 +368,23 @@ static int nl_kernel(int id, int dim, double complex *r, const double complex *i
         for (int d = 0; d < dim; ++d) r[1 + d] = in[1 + d];
         return 0;
     }
+    case ORA_NL_NLPOISSON105: { /* u, grad u ; result[1] = exp(u) - exp(-u) ; result[2] = eps * grad u */
+        r[0] = cexp(in[0]) - cexp(-in[0]);
+        for (int d = 0; d < dim; ++d) r[1 + d] = p[0] * in[1 + d];
+        return 0;
+    }
+    case ORA_NL_STVENANT230: { /* input = grad(u) as a vector, Voigt strain, isotropic stress, per-region material */
+        int R = (int)p[0], reg = qp->region >= 1 && qp->region <= R ? qp->region - 1 : 0;
+        double la = p[1 + reg], mu = p[1 + R + reg], eT = p[1 + 2 * R + reg];
+        double complex e1 = in[0], e2 = in[3], e3 = in[1] + in[2];
+        e1 += 0.5 * (in[0] * in[0] + in[2] * in[2]);
+        e2 += 0.5 * (in[1] * in[1] + in[3] * in[3]);
+        e3 += in[0] * in[1] + in[2] * in[3];
+        e1 -= eT; e2 -= eT;
+        double complex a = la * (e1 + e2) + 2 * mu * e1, b = la * (e1 + e2) + 2 * mu * e2, c = 2 * mu * e3;
+        r[0] = a; r[1] = c; r[2] = c; r[3] = b;
+        return 0;
+    }
     }
     return -1;
 }
@@ -397,9 +444,11 @@ static int csc_add(ora_csc *A, int64_t i, int64_t j, double v)
     return -2;
 }
 
+
 typedef struct { ora_coo *coo; ora_csc *csc; } ora_sink;
 static int sink_add(ora_sink *s, int64_t i, int64_t j, double v)
 {
+    v = ORA_ACC(v);
     if (s->csc) return csc_add(s->csc, i, j, v);
     return coo_push(s->coo, i, j, v);
 }
@@ -465,16 +514,17 @@ int ora_assemble_bilinear(const ora_mesh *m, int ntest, const ora_arg *test, int
                     for (int j = 0; j < nd_g[id]; ++j) {
                         int64_t dof = args[id].celldofs[item * nd_g[id] + j] - 1 + args_sol_offsets[id];
                         for (int d = 0; d < oplen_g[id]; ++d)
-                            input_args[d + off_g[id]] += sol[dof] * cv_g[id][((size_t)q * nd_g[id] + j) * oplen_g[id] + d];
+                            input_args[d + off_g[id]] += ORA_ACC(sol[dof]) * cv_g[id][((size_t)q * nd_g[id] + j) * oplen_g[id] + d];
                     }
             }
-            eval_trafo(qp.x, &T, qx + (size_t)q * dim, dim);
+            eval_trafo(qp.x, &T, qx + (size_t)q * m->tdim, dim, m->tdim);
             for (int id = 0; id < nansatz; ++id) {
                 for (int j = 0; j < nd_a[id]; ++j) {
                     for (int d = 0; d < off_a[nansatz]; ++d) input_ansatz[d] = 0;
                     for (int d = 0; d < oplen_a[id]; ++d)
                         input_ansatz[d + off_a[id]] = cv_a[id][((size_t)q * nd_a[id] + j) * oplen_a[id] + d];
                     if (bl_kernel(kernel_id, dim, result, input_ansatz, input_args, &qp, off_t[ntest])) { rc = -3; goto done; }
+                    ora_abs_vec(result, off_t[ntest]);
                     for (int d = 0; d < off_t[ntest]; ++d) result[d] *= factor * qw[q];
                     if (lump == 1) {
                         for (int d = 0; d < oplen_t[id]; ++d)
@@ -579,21 +629,22 @@ int ora_assemble_linear(const ora_mesh *m, int ntest, const ora_arg *test, int n
                     for (int j = 0; j < nd_g[id]; ++j) {
                         int64_t dof = args[id].celldofs[item * nd_g[id] + j] - 1 + args_sol_offsets[id];
                         for (int d = 0; d < oplen_g[id]; ++d)
-                            input_args[d + off_g[id]] += sol[dof] * cv_g[id][((size_t)q * nd_g[id] + j) * oplen_g[id] + d];
+                            input_args[d + off_g[id]] += ORA_ACC(sol[dof]) * cv_g[id][((size_t)q * nd_g[id] + j) * oplen_g[id] + d];
                     }
             }
-            eval_trafo(qp.x, &T, qx + (size_t)q * dim, dim);
+            eval_trafo(qp.x, &T, qx + (size_t)q * m->tdim, dim, m->tdim);
             if (nargs > 0) {
                 if (kernel_id != ORA_BLK_STANDARD) { rc = -3; break; }
                 for (int d = 0; d < oplen; ++d) result[d] = input_args[d];
             } else if (lin_kernel(kernel_id, result, &qp, oplen,
                                   tabulated ? tabulated + ((size_t)item * nq + q) * oplen : NULL)) { rc = -3; break; }
+            ora_abs_vec(result, oplen);
             for (int d = 0; d < oplen; ++d) result[d] *= factor * qw[q] * m->cellvolumes[item];
             for (int idt = 0; idt < ntest; ++idt)
                 for (int k = 0; k < nd_t[idt]; ++k) {
                     int64_t dof = test[idt].celldofs[item * nd_t[idt] + k] - 1 + test[idt].offset;
                     for (int d = 0; d < oplen_t[idt]; ++d)
-                        b[dof] += result[d + off_t[idt]] * cv_t[idt][((size_t)q * nd_t[idt] + k) * oplen_t[idt] + d];
+                        b[dof] += ORA_ACC(result[d + off_t[idt]] * cv_t[idt][((size_t)q * nd_t[idt] + k) * oplen_t[idt] + d]);
                 }
         }
     }
@@ -648,9 +699,9 @@ int ora_assemble_nonlinear(const ora_mesh *m, int ntest, const ora_arg *test, in
                 for (int j = 0; j < nd_g[id]; ++j) {
                     int64_t dof = args[id].celldofs[item * nd_g[id] + j] - 1 + args_sol_offsets[id];
                     for (int d = 0; d < oplen_g[id]; ++d)
-                        input_args[d + off_g[id]] += sol[dof] * cv_g[id][((size_t)q * nd_g[id] + j) * oplen_g[id] + d];
+                        input_args[d + off_g[id]] += ORA_ACC(sol[dof]) * cv_g[id][((size_t)q * nd_g[id] + j) * oplen_g[id] + d];
                 }
-            eval_trafo(qp.x, &T, qx + (size_t)q * dim, dim);
+            eval_trafo(qp.x, &T, qx + (size_t)q * m->tdim, dim, m->tdim);
             {   /* value_and_jacobian! (:358-365) */
                 double complex zin[ORA_MAXOP], zout[ORA_MAXOP];
                 const double h = 1e-40;
@@ -663,6 +714,8 @@ int ora_assemble_nonlinear(const ora_mesh *m, int ntest, const ora_arg *test, in
                     for (int k = 0; k < nout; ++k) jac[k * nin + j] = cimag(zout[k]) / h;
                     zin[j] = input_args[j];
                 }
+                ora_abs_vec(value, nout);
+                ora_abs_vec(jac, nin * nout);
             }
             /* update matrix (:372-401) */
             for (int id = 0; id < nargs; ++id)
@@ -681,13 +734,13 @@ int ora_assemble_nonlinear(const ora_mesh *m, int ntest, const ora_arg *test, in
             for (int k = 0; k < nout; ++k) {
                 double s = 0;
                 for (int d = 0; d < nin; ++d) s += jac[k * nin + d] * input_args[d];
-                tempV[k] = (s - value[k]) * (factor * qw[q] * vol);
+                tempV[k] = (g_abs_accumulate ? s + value[k] : s - value[k]) * (factor * qw[q] * vol);
             }
             for (int idt = 0; idt < ntest; ++idt)
                 for (int j = 0; j < nd_t[idt]; ++j) {
                     int64_t dof = test[idt].celldofs[item * nd_t[idt] + j] - 1 + test[idt].offset;
                     for (int d = 0; d < oplen_t[idt]; ++d)
-                        b[dof] += tempV[d + off_t[idt]] * cv_t[idt][((size_t)q * nd_t[idt] + j) * oplen_t[idt] + d];
+                        b[dof] += ORA_ACC(tempV[d + off_t[idt]] * cv_t[idt][((size_t)q * nd_t[idt] + j) * oplen_t[idt] + d]);
                 }
         }
         for (int id = 0; id < nargs; ++id)
@@ -709,6 +762,62 @@ done:
     for (int j = 0; j < ntest; ++j) free(cv_t[j]);
     for (int j = 0; j < nargs; ++j) free(cv_g[j]);
     for (int j = 0; j < ntest; ++j) for (int k = 0; k < nargs; ++k) free(Aloc[j][k]);
+    return rc;
+}
+
+/* =====================================================================================
+ * ItemIntegrator assembly_loop  (item_integrator.jl:191-249): piecewise b[1:resultdim, item] += kernel(...) * factor*w*|T|
+ * ===================================================================================== */
+int ora_integrate(const ora_mesh *m, int nargs, const ora_arg *args, const double *sol, const int64_t *args_sol_offsets,
+                  int nq, const double *qw, const double *qx, int kernel_id, const double *params, int nparams, double factor,
+                  double time, const int32_t *regions, int nregions, const double *tabulated /* [ncells][nq][resultdim] */,
+                  int resultdim, double *b /* [ncells][resultdim] */)
+{
+    int dim = m->dim;
+    int oplen_g[ORA_MAXARGS], off_g[ORA_MAXARGS + 1] = {0}, nd_g[ORA_MAXARGS];
+    double *cv_g[ORA_MAXARGS];
+    for (int j = 0; j < nargs; ++j) {
+        oplen_g[j] = arg_oplen(&args[j], dim); off_g[j + 1] = off_g[j] + oplen_g[j]; nd_g[j] = arg_ndofs(&args[j]);
+        cv_g[j] = malloc(sizeof(double) * (size_t)nq * nd_g[j] * oplen_g[j]);
+    }
+    int nin = off_g[nargs], rc = 0;
+    double input_args[ORA_MAXOP], result[ORA_MAXOP];
+    ora_qpinfo qp;
+    memset(&qp, 0, sizeof qp);
+    qp.params = params; qp.nparams = nparams; qp.time = time;
+    ora_trafo T;
+    for (int64_t item = 0; item < m->ncells && !rc; ++item) {
+        int reg = m->cellregions[item];
+        if (reg > 0 && !region_visited(regions, nregions, reg)) continue;
+        qp.region = reg; qp.item = item + 1; qp.volume = m->cellvolumes[item];
+        update_trafo(&T, m, item);
+        for (int j = 0; j < nargs; ++j) update_basis(cv_g[j], &args[j], &T, dim, nq);
+        for (int q = 0; q < nq; ++q) {
+            for (int d = 0; d < nin; ++d) input_args[d] = 0;
+            for (int id = 0; id < nargs; ++id)
+                for (int j = 0; j < nd_g[id]; ++j) {
+                    int64_t dof = args[id].celldofs[item * nd_g[id] + j] - 1 + args_sol_offsets[id];
+                    for (int d = 0; d < oplen_g[id]; ++d)
+                        input_args[d + off_g[id]] += ORA_ACC(sol[dof]) * cv_g[id][((size_t)q * nd_g[id] + j) * oplen_g[id] + d];
+                }
+            eval_trafo(qp.x, &T, qx + (size_t)q * m->tdim, dim, m->tdim);
+            switch (kernel_id) {
+            case ORA_II_STANDARD: for (int d = 0; d < resultdim; ++d) result[d] = d < nin ? input_args[d] : 0; break;
+            case ORA_II_L2NORM: for (int d = 0; d < resultdim; ++d) result[d] = d < nin ? input_args[d] * input_args[d] : 0; break;
+            case ORA_II_L2DIFF_TABULATED:
+                for (int d = 0; d < resultdim; ++d) {
+                    double e = tabulated[((size_t)item * nq + q) * resultdim + d] - input_args[d];
+                    result[d] = e * e;
+                }
+                break;
+            case ORA_II_L2ERR_SINCOS301: { double e = sin(1.7 * qp.x[0]) * cos(3.9 * qp.x[1]) - input_args[0]; result[0] = e * e; } break;
+            case ORA_II_L2ERR_EXP108: { double e = exp(qp.x[0]) - input_args[0]; result[0] = e * e; } break;
+            default: rc = -3;
+            }
+            for (int d = 0; d < resultdim; ++d) b[item * resultdim + d] += result[d] * (factor * qw[q] * m->cellvolumes[item]);
+        }
+    }
+    for (int j = 0; j < nargs; ++j) free(cv_g[j]);
     return rc;
 }
 

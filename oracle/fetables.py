@@ -43,6 +43,8 @@ def _gauss_jacobi_01(n, alpha):
 
 def quadrature_rule(dim: int, order: int):
     """Returns (xref [nq, dim], w [nq]) with sum(w) == 1."""
+    if dim == 0:                 # a vertex: the boundary "face" of a 1D grid
+        return np.zeros((1, 0)), np.array([1.0])
     if dim == 1:
         if order <= 1:
             return np.array([[0.5]]), np.array([1.0])
@@ -87,6 +89,34 @@ def quadrature_rule(dim: int, order: int):
     raise ValueError(dim)
 
 
+def _ref_basis_p3(lam, dlam):
+    """Cubic Lagrange basis (H1Pk order 3; engine convention, see extendablefem.jl_b200/host/fespace.py): vertices,
+    then two dofs per edge (a,b) at 1/3 and 2/3 from a towards b, then (2D) the cell bubble / (3D) one dof per face
+    (faces (0,1,2),(0,1,3),(1,2,3),(0,2,3) would be needed in 3D: only dim <= 2 is provided here)."""
+    nq, nv = lam.shape
+    dim = nv - 1
+    edges = {1: ((0, 1),), 2: TRI_EDGES}[dim]
+    nb = nv + 2 * len(edges) + (1 if dim == 2 else 0)
+    vals = np.zeros((nq, nb)); grads = np.zeros((nq, nb, dim))
+    for i in range(nv):
+        l = lam[:, i]
+        vals[:, i] = 0.5 * l * (3 * l - 1) * (3 * l - 2)
+        grads[:, i, :] = (0.5 * (27 * l * l - 18 * l + 2))[:, None] * dlam[i][None, :]
+    k = nv
+    for (a, b) in edges:
+        la, lb = lam[:, a], lam[:, b]
+        for (p, q, dp, dq) in ((la, lb, dlam[a], dlam[b]), (lb, la, dlam[b], dlam[a])):
+            # 9/2 p q (3p - 1): equals 1 at p = 2/3, q = 1/3
+            vals[:, k] = 4.5 * p * q * (3 * p - 1)
+            grads[:, k, :] = 4.5 * ((q * (6 * p - 1))[:, None] * dp[None, :] + (p * (3 * p - 1))[:, None] * dq[None, :])
+            k += 1
+    if dim == 2:
+        vals[:, k] = 27 * lam[:, 0] * lam[:, 1] * lam[:, 2]
+        grads[:, k, :] = 27 * ((lam[:, 1] * lam[:, 2])[:, None] * dlam[0][None, :] + (lam[:, 0] * lam[:, 2])[:, None] * dlam[1][None, :]
+                               + (lam[:, 0] * lam[:, 1])[:, None] * dlam[2][None, :])
+    return vals, grads
+
+
 def barycentric(xref: np.ndarray):
     """lambda [nq, dim+1] and constant reference gradients dlam [dim+1, dim]."""
     nq, dim = xref.shape
@@ -99,7 +129,11 @@ def ref_basis(order: int, xref: np.ndarray):
     """Scalar H1 Lagrange basis on the reference simplex.
     Returns vals [nq, nb], grads [nq, nb, dim]."""
     nq, dim = xref.shape
+    if dim == 0:
+        return np.ones((nq, 1)), np.zeros((nq, 1, 0))
     lam, dlam = barycentric(xref)
+    if order == 3:
+        return _ref_basis_p3(lam, dlam)
     if order == 1:
         vals = lam.copy()
         grads = np.broadcast_to(dlam[None], (nq, dim + 1, dim)).copy()

@@ -21,9 +21,10 @@ _LIB_PATH = os.path.join(_HERE, "liboracle_ref.so")
 _lib = None
 
 OP_ID, OP_GRAD, OP_DIV, OP_SYMGRAD_VOIGT = 0, 1, 2, 3
-BLK = dict(standard=1, dcr=2, stokes=3, linnse7=4, hooke_grad=5, hooke_voigt=6, convect_args=7)
-LIN = dict(constant_one=1, constant_params=2, xy=3, sincos301=4, tabulated=5)
-NL = dict(nse2d=1, linnse7=2, neohooke3d=3, rcd=4)
+BLK = dict(standard=1, dcr=2, stokes=3, linnse7=4, hooke_grad=5, hooke_voigt=6, convect_args=7, robin108=8)
+LIN = dict(constant_one=1, constant_params=2, xy=3, sincos301=4, tabulated=5, exp2x=6, step105=7)
+NL = dict(nse2d=1, linnse7=2, neohooke3d=3, rcd=4, nlpoisson105=5, stvenant230=6)
+II = dict(ii_standard=1, l2norm=2, l2diff_tabulated=3, l2err_sincos301=4, l2err_exp108=5)
 
 
 def build(force: bool = False) -> str:
@@ -36,7 +37,7 @@ def build(force: bool = False) -> str:
 class _Mesh(C.Structure):
     _fields_ = [("dim", C.c_int), ("ncells", C.c_int64), ("nnodes", C.c_int64),
                 ("coords", C.c_void_p), ("cellnodes", C.c_void_p),
-                ("cellregions", C.c_void_p), ("cellvolumes", C.c_void_p)]
+                ("cellregions", C.c_void_p), ("cellvolumes", C.c_void_p), ("tdim", C.c_int)]
 
 
 class _Arg(C.Structure):
@@ -64,6 +65,17 @@ def lib():
     return _lib
 
 
+class abs_accumulate:
+    """Context manager: inside it every assembly accumulates |contribution| instead of the contribution, i.e. returns the
+    entrywise scale of a backward-error comparison (tests/util.py: check_values_entrywise)."""
+
+    def __enter__(self):
+        lib().ora_set_abs_accumulate(1)
+
+    def __exit__(self, *exc):
+        lib().ora_set_abs_accumulate(0)
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -80,26 +92,40 @@ class OraArg:
 
 
 class Mesh:
+    """Items of one assembly type: the cells of a grid, or (cellnodes = BFaceNodes etc.) its boundary faces,
+    whose topological dimension ``tdim`` is one less than the space dimension (bilinear_operator.jl:693-714)."""
+
     def __init__(self, coords, cellnodes, cellregions=None, cellvolumes=None):
         self.coords = np.ascontiguousarray(coords, dtype=np.float64)
         self.cellnodes = np.ascontiguousarray(cellnodes, dtype=np.int32)
         nc = self.cellnodes.shape[0]
+        self.dim = self.coords.shape[1]
+        self.tdim = self.cellnodes.shape[1] - 1
+        assert self.tdim in (self.dim, self.dim - 1)
         self.cellregions = np.ascontiguousarray(
             np.ones(nc, np.int32) if cellregions is None else cellregions, dtype=np.int32)
         if cellvolumes is None:
-            x = self.coords[self.cellnodes.astype(np.int64) - 1]
             import math
-            cellvolumes = np.abs(np.linalg.det(x[:, 1:, :] - x[:, :1, :])) / math.factorial(self.coords.shape[1])
+            x = self.coords[self.cellnodes.astype(np.int64) - 1]
+            e = x[:, 1:, :] - x[:, :1, :]
+            if self.tdim == self.dim:
+                cellvolumes = np.abs(np.linalg.det(e)) / math.factorial(self.dim)
+            elif self.tdim == 0:
+                cellvolumes = np.ones(nc)
+            else:
+                gram = np.einsum("nik,njk->nij", e, e)
+                cellvolumes = np.sqrt(np.abs(np.linalg.det(gram))) / math.factorial(self.tdim)
         self.cellvolumes = np.ascontiguousarray(cellvolumes, dtype=np.float64)
-        self.dim = self.coords.shape[1]
         self.ncells = nc
         self.c = _Mesh(self.dim, nc, self.coords.shape[0], _ptr(self.coords), _ptr(self.cellnodes),
-                       _ptr(self.cellregions), _ptr(self.cellvolumes))
+                       _ptr(self.cellregions), _ptr(self.cellvolumes), self.tdim)
 
 
-def _make_args(args, xref):
+def _make_args(args, xref, mesh=None):
     keep, arr = [], (_Arg * max(1, len(args)))()
     for i, a in enumerate(args):
+        if mesh is not None and mesh.tdim < mesh.dim:
+            assert a.op == OP_ID, "boundary faces: Identity operators only"
         vals, grads = fetables.ref_basis(a.order, xref)
         vals = np.ascontiguousarray(vals); grads = np.ascontiguousarray(grads)
         cd = np.ascontiguousarray(a.celldofs, dtype=np.int32)
@@ -145,9 +171,9 @@ def assemble_bilinear(mesh: Mesh, test, ansatz, kernel="standard", params=(), fa
     dim = mesh.dim
     if quadorder == "auto":
         quadorder = max(polyorder(a) for a in ansatz) + max(polyorder(a) for a in test)
-    xref, w = fetables.quadrature_rule(dim, quadorder + bonus_quadorder)
+    xref, w = fetables.quadrature_rule(mesh.tdim, quadorder + bonus_quadorder)
     xref = np.ascontiguousarray(xref); w = np.ascontiguousarray(w)
-    ta, k1 = _make_args(test, xref); aa, k2 = _make_args(ansatz, xref); ga, k3 = _make_args(args, xref)
+    ta, k1 = _make_args(test, xref, mesh); aa, k2 = _make_args(ansatz, xref, mesh); ga, k3 = _make_args(args, xref, mesh)
     if coupling is None:
         coupling = np.ones((len(ansatz), len(test)), np.uint8)
     coupling = np.ascontiguousarray(coupling, dtype=np.uint8)
@@ -181,9 +207,9 @@ def assemble_linear(mesh: Mesh, test, b, kernel="constant_one", params=(), facto
     dim = mesh.dim
     if quadorder == "auto":
         quadorder = max(polyorder(a) for a in test) + (max(polyorder(a) for a in args) if args else 0)
-    xref, w = fetables.quadrature_rule(dim, quadorder + bonus_quadorder)
+    xref, w = fetables.quadrature_rule(mesh.tdim, quadorder + bonus_quadorder)
     xref = np.ascontiguousarray(xref); w = np.ascontiguousarray(w)
-    ta, k1 = _make_args(test, xref); ga, k3 = _make_args(args, xref)
+    ta, k1 = _make_args(test, xref, mesh); ga, k3 = _make_args(args, xref, mesh)
     p = np.ascontiguousarray(np.asarray(params, dtype=np.float64))
     r, nr = _regions(regions)
     so = np.ascontiguousarray(np.asarray(args_sol_offsets, dtype=np.int64))
@@ -203,9 +229,9 @@ def assemble_nonlinear(mesh: Mesh, test, args, sol, b, kernel, params=(), factor
     dim = mesh.dim
     if quadorder == "auto":
         quadorder = max(polyorder(a) for a in args) + max(polyorder(a) for a in test)
-    xref, w = fetables.quadrature_rule(dim, quadorder + bonus_quadorder)
+    xref, w = fetables.quadrature_rule(mesh.tdim, quadorder + bonus_quadorder)
     xref = np.ascontiguousarray(xref); w = np.ascontiguousarray(w)
-    ta, k1 = _make_args(test, xref); ga, k3 = _make_args(args, xref)
+    ta, k1 = _make_args(test, xref, mesh); ga, k3 = _make_args(args, xref, mesh)
     p = np.ascontiguousarray(np.asarray(params, dtype=np.float64))
     r, nr = _regions(regions)
     if args_sol_offsets is None:
@@ -229,6 +255,44 @@ def assemble_nonlinear(mesh: Mesh, test, args, sol, b, kernel, params=(), factor
     assert rc == 0, rc
     n = coo.n
     return coo_to_csc(I[:n], J[:n], V[:n], shape), b
+
+
+def integrate(mesh: Mesh, args, sol, kernel="ii_standard", params=(), factor=1.0, quadorder="auto", bonus_quadorder=0,
+              regions=None, resultdim=0, args_sol_offsets=None, time=0.0, tabulated=None, piecewise=True):
+    """ItemIntegrator ``evaluate`` (item_integrator.jl:323-352): [ncells, resultdim] (piecewise) or [resultdim]."""
+    if quadorder == "auto":
+        quadorder = max(polyorder(a) for a in args)
+    xref, w = fetables.quadrature_rule(mesh.tdim, quadorder + bonus_quadorder)
+    xref = np.ascontiguousarray(xref); w = np.ascontiguousarray(w)
+    ga, k3 = _make_args(args, xref, mesh)
+    nin = sum(oplen(a, mesh.dim) for a in args)
+    if resultdim == 0:
+        resultdim = nin
+    p = np.ascontiguousarray(np.asarray(params, dtype=np.float64))
+    r, nr = _regions(regions)
+    if args_sol_offsets is None:
+        args_sol_offsets = [a.offset for a in args]
+    so = np.ascontiguousarray(np.asarray(args_sol_offsets, dtype=np.int64))
+    solp = np.ascontiguousarray(sol, dtype=np.float64)
+    tab = None if tabulated is None else np.ascontiguousarray(tabulated, dtype=np.float64)
+    b = np.zeros((mesh.ncells, resultdim))
+    rc = lib().ora_integrate(C.byref(mesh.c), len(args), ga, _ptr(solp), _ptr(so), w.size, _ptr(w), _ptr(xref), II[kernel],
+                             _ptr(p), p.size, C.c_double(factor), C.c_double(time), _ptr(r), nr, _ptr(tab), resultdim, _ptr(b))
+    assert rc == 0, rc
+    if piecewise:
+        return b
+    out = np.zeros(resultdim)
+    for row in b:                      # b .+= result_kernel in item order (item_integrator.jl:241-243)
+        out += row
+    return out
+
+
+def quadrature_points(mesh: Mesh, quadorder):
+    """x at the quadrature points of every item: [nitems, nq, dim] (what a host evaluates tabulated closures at)."""
+    xref, w = fetables.quadrature_rule(mesh.tdim, quadorder)
+    lam, _ = fetables.barycentric(xref) if mesh.tdim > 0 else (np.ones((1, 1)), None)
+    x = mesh.coords[mesh.cellnodes.astype(np.int64) - 1]          # [n, tdim+1, dim]
+    return np.einsum("qv,nvd->nqd", lam, x)
 
 
 def nl_value_and_jacobian(kernel, dim, x, nout, params=()):
