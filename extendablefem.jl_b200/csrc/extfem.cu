@@ -75,6 +75,8 @@ struct TemplatePlan {
     std::unique_ptr<JitModule> jit;
     DevBuf jit_live[2];              // launch-order warps of the short- / long-column class
     int jit_nlive[2] = {0, 0};
+    DevBuf walk;                     // walk records of the templates (walkplan.h), [nrounds][TW_RW] words, same round indices
+    bool walk_ok = false;
 };
 
 struct Pattern {
@@ -134,8 +136,10 @@ struct Ctx {
     long long jit_mincols = 200000; // option "template_jit_min_cols": smallest column block that is worth the compile time
     bool tmpl_planemask = true; // option "template_plane_mask": rounds load only the geometry values their local column reads
     bool tmpl_const = true;     // option "template_constant_memory": template rounds in constant memory when they fit
+    bool tmpl_walk = true;      // option "template_walk": 3D P2 columns run as walk programs (walkplan.h) when every template verifies
     bool tmpl_permute_mesh = true; // option "template_permute_mesh": cell kernels read mesh copies in the transposed order
     int tmpl_mincols = 24;      // option "template_min_cols": smallest group of columns that gets a template
+    int tmpl_classmask = 3;     // option "template_class_mask": tuning aid (time the short- / long-column warps alone)
     bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator
     long long launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -906,6 +910,34 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
             jt.words.assign(hwords.begin() + (size_t)jt.r0 * TP_TW, hwords.begin() + (size_t)(jt.r0 + jt.m) * TP_TW);
             T.jtmpl.push_back(std::move(jt));
         }
+        // walk programs of 3D P2 columns (walkplan.h): all templates must plan and verify, else the plan keeps the
+        // read-modify-write kernel
+        T.walk_ok = false;
+        if (ctx->tmpl_walk && M.dim == 3 && S.order == 2 && S.fetype == EXTFEM_FE_H1P2 && ns == 10 && nrounds <= TP_CONST_ROUNDS) {
+            std::vector<unsigned> wrec((size_t)nrounds * TW_RW, 0u), one;
+            bool ok = true;
+            for (const JitTemplate &jt : T.jtmpl) {
+                WalkTemplateIn W;
+                W.m = jt.m; W.L = jt.L;
+                for (int i = 0; i < jt.m && ok; ++i) {
+                    const unsigned *w = &jt.words[(size_t)i * TP_TW];
+                    W.celloff.push_back((int)w[0]);
+                    W.kl.push_back((int)(w[1] & 0xff));
+                    W.orient.push_back((int)((w[1] >> 20) & 1u));
+                    std::array<int, 10> pp;
+                    for (int t = 0; t < 10; ++t) { pp[t] = (int)(w[2 + t] / (TP_LD * 8)); ok = ok && pp[t] < jt.L; }
+                    W.pos.push_back(pp);
+                }
+                ok = ok && tw_plan_template(W, Lg.Npad, one);
+                if (!ok) break;
+                std::copy(one.begin(), one.end(), wrec.begin() + (size_t)jt.r0 * TW_RW);
+            }
+            if (ok) {
+                if (int rc = upload(ctx, T.walk, wrec.data(), wrec.size() * 4)) return rc;
+                EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+                T.walk_ok = true;
+            }
+        }
         std::vector<int> live[2];
         for (size_t i = 0; i < launch.size(); ++i)
             if (tp_desc_m(launch[i].y) > 0) live[tp_desc_L(launch[i].y) > JIT_SPLIT_L ? 1 : 0].push_back((int)i);
@@ -1028,7 +1060,7 @@ static int launch_template(Ctx *ctx, Pattern &P, TemplatePlan &T, int b, int acc
     TPArgs A;
     A.wdesc = T.wdesc.as<int4>(); A.slotpb = T.slotpb.as<int>(); A.slotptr = T.slotptr.as<double *>();
     A.tmpl = T.tmpl.as<unsigned>(); A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
-    A.nwarps = T.nctas * TP_MAXW; A.ahead = ctx->tmpl_ahead * TP_MAXW;
+    A.nwarps = T.nctas * TP_MAXW; A.ahead = ctx->tmpl_ahead * TP_MAXW; A.classmask = ctx->tmpl_classmask;
     (void)P; (void)b;
     auto k = tp_gather_kernel<EV, FIRST, CT>;
     if (int rc = smem_attr(ctx, (const void *)k, 227 * 1024)) return rc;
@@ -1084,7 +1116,27 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
             jit_done = true;
         }
     }
-    if (SOA && T.nwarps > 0 && !jit_done) {
+    bool walk_done = false;
+    if (SOA && T.nwarps > 0 && !jit_done && std::is_same<EV, EvalBary<3, 2>>::value && T.walk_ok && ctx->tmpl_walk) {
+        // walk programs (walkplan.h): records live in the constant bank of the templates
+        const bool first = !accumulate && P.rowspaces.size() == 1;
+        const void *owner = (const char *)&T + 1;
+        if (g_const_tmpl_owner[ctx->device % EXTFEM_MAXDEV] != owner) {
+            EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_tmpl, T.walk.p, (size_t)T.nrounds * TW_RW * 4, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+            g_const_tmpl_owner[ctx->device % EXTFEM_MAXDEV] = owner;
+        }
+        TPArgs A;
+        A.wdesc = T.wdesc.as<int4>(); A.slotpb = T.slotpb.as<int>(); A.slotptr = T.slotptr.as<double *>();
+        A.tmpl = T.walk.as<unsigned>(); A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
+        A.nwarps = T.nctas * TP_MAXW; A.ahead = ctx->tmpl_ahead * TP_MAXW; A.classmask = ctx->tmpl_classmask;
+        auto k = first ? tw_gather_kernel<true> : tw_gather_kernel<false>;
+        if (int rc = smem_attr(ctx, (const void *)k, 227 * 1024)) return rc;
+        k<<<T.nctas, TP_MAXW * 32, T.pool_bytes, ctx->stream>>>(A);
+        LAUNCHED(ctx);
+        EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
+        walk_done = true;
+    }
+    if (SOA && T.nwarps > 0 && !jit_done && !walk_done) {
         // first-touch stores need: overwrite, and column segments that hold rows of this block only
         const bool first = !accumulate && P.rowspaces.size() == 1;
         // templates in constant memory when they fit (re-uploaded when another plan used the bank in between)
@@ -1693,8 +1745,10 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "template_jit_min_cols")) { C->jit_mincols = value < 0 ? 0 : value; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_plane_mask")) { C->tmpl_planemask = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_constant_memory")) { C->tmpl_const = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_walk")) { C->tmpl_walk = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_permute_mesh")) { C->tmpl_permute_mesh = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_min_cols")) { C->tmpl_mincols = value < 1 ? 1 : value; return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_class_mask")) { C->tmpl_classmask = value & 3; return EXTFEM_OK; }
     return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("unknown option ") + (key ? key : "(null)"));
 }
 

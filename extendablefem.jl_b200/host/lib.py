@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libextfem_cuda.so")
+LIB_PATH = os.environ.get("EXTFEM_LIB", os.path.join(os.path.dirname(_HERE), "csrc", "libextfem_cuda.so"))
 
 MAXARGS = 4
 OP_ID, OP_GRAD, OP_DIV, OP_SYMGRAD_VOIGT = 0, 1, 2, 3
