@@ -70,40 +70,100 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def build_problem(pkg, n, rank=0, world=1):
-    """Structured unit-cube grid (6 tets per cube); rank r of a multi-GPU run gets the z-slab
-    [r, r+1] of the stacked domain [0,1]^2 x [0,world] (weak scaling, no data-path collective)."""
+def build_problem(pkg, n, rank=0, world=1, scaling="weak"):
+    """Structured grid simplexgrid(0:1/n:1, 0:1/n:1, 0:1/n:nz/n) (6 tets per cube) cut into z-slabs of whole cube layers, one per
+    rank.  weak: nz = n * world (every rank owns an n^3-cube slab); strong: nz = n (ONE n^3 mesh shared by all ranks).  With
+    world > 1 the local mesh carries one zero-volume ghost layer per neighbour (host/dist.py: SlabShard)."""
+    nz = n * world if scaling == "weak" else n
+    ranges = pkg.layer_ranges(nz, world)
+    sh = pkg.SlabShard(pkg, n, nz, ranges, rank)
+    return sh
+
+
+def lattice_keys(FES, n):
+    """Global integer lattice id of every scalar dof (nodes at even, edge midpoints at odd doubled coordinates)."""
+    pts = FES.dof_coordinates()
+    q = np.rint(pts * 2 * n).astype(np.int64)
+    w = 2 * n + 1
+    return (q[:, 2] * w + q[:, 1]) * w + q[:, 0]
+
+
+def algorithmic_bytes(dim, nd, ncells, nnz):
+    """coordinates + dof ids read + matrix values written once."""
+    return (8 * dim * (dim + 1) + 4 * nd) * ncells + 8 * nnz
+
+
+def parity_vs_oracle(pkg, eng, pat, n, nzl, keys_engine, colptr, planes):
+    """Full-size parity (outside the timed region): the engine's device-resident columns of all dofs on a few z-planes of the
+    benchmark mesh against the CPU oracle run on the two cube layers around each plane (every cell adjacent to such a dof lies in
+    them).  Returns max |engine - oracle| / max |oracle| over the compared entries."""
+    from oracle import oracle as ora
+    ora.build()
+    nzval, _ = eng.values_get(pat, want_b=False)
+    order = np.argsort(keys_engine)
+    skeys = keys_engine[order]
+    worst, count, ref_max = 0.0, 0, 0.0
+    h = 1.0 / n
     X = np.linspace(0.0, 1.0, n + 1)
-    Z = np.linspace(float(rank), float(rank + 1), n + 1)
-    grid = pkg.simplexgrid(X, X, Z)
-    FES = pkg.FESpace(pkg.H1P2(1, 3), grid)
-    return grid, FES
+    for k in planes:
+        l0, l1 = max(0, k - 1), min(nzl, k + 1)
+        g = pkg.simplexgrid(X, X, h * np.arange(l0, l1 + 1))
+        F = pkg.FESpace(pkg.H1P2(1, 3), g)
+        keys = lattice_keys(F, n)
+        om = ora.Mesh(g.coords, g.cellnodes, g.cellregions, g.cellvolumes)
+        gr = ora.OraArg(F.celldofs, 1, 2, ora.OP_GRAD)
+        cp, rv = ora.structural_pattern([gr], [gr], (F.ndofs, F.ndofs))
+        ref = ora.assemble_bilinear(om, [gr], [gr], "standard", csc=(cp, rv))
+        w = 2 * n + 1
+        cols = np.nonzero(keys // (w * w) == 2 * k)[0]                  # dofs on the plane z = k h
+        gcol = order[np.searchsorted(skeys, keys[cols])]
+        assert np.array_equal(keys_engine[gcol], keys[cols])
+        for c, gc in zip(cols, gcol):
+            a = ref[cp[c] - 1:cp[c + 1] - 1]
+            b = nzval[colptr[gc] - 1:colptr[gc + 1] - 1]
+            assert a.size == b.size, "pattern of a benchmark column differs from the oracle's"
+            worst = max(worst, float(np.abs(a - b).max()))
+            ref_max = max(ref_max, float(np.abs(a).max()))
+            count += a.size
+    return {"max_rel": worst / ref_max, "entries_checked": int(count), "planes_z_index": [int(k) for k in planes],
+            "against": "CPU oracle (oracle/assembly_ref.c) on the cube layers around each plane"}
 
 
-def slab_interfaces(pkg, FES, rank, world):
-    """Interface plan of the stacked slabs: the top plane of rank r is the bottom plane of rank r+1 (dofs matched by
-    their coordinates, ordered lexicographically in (y, x)); the lower rank owns the shared plane."""
-    xyz = FES.dof_coordinates()
-    z = xyz[:, 2]
-    neigh, ptr, rows = [], [0], []
-    owned = np.ones(FES.ndofs, dtype=np.uint8)
-    for r, zz in ((rank - 1, z.min()), (rank + 1, z.max())):
-        if r < 0 or r >= world:
-            continue
-        idx = np.nonzero(z == zz)[0]
-        idx = idx[np.lexsort((xyz[idx, 0], xyz[idx, 1]))]
-        neigh.append(r); rows.append(idx.astype(np.int64) + 1); ptr.append(ptr[-1] + idx.size)
-        if r < rank:
-            owned[idx] = 0
-    return pkg.InterfacePlan(rank, world, np.asarray(neigh, dtype=np.int32), np.asarray(ptr, dtype=np.int64),
-                             np.concatenate(rows), owned)
-
-
-def algorithmic_bytes(grid, FES, nnz):
-    """coordinates + dof ids read + matrix values written once (+ rhs written)."""
-    dim = grid.dim
-    per_cell = 8 * dim * (dim + 1) + 4 * FES.ndofs4cell
-    return per_cell * grid.ncells + 8 * nnz
+def parity_vs_single_gpu(pkg, eng, sh, pat, colptr):
+    """Strong scaling: the owned columns of this rank after the interface reduction against the SAME mesh assembled on this GPU
+    alone (one context, no partition): entrywise, every column within two layers of a partition interface plus a random sample
+    of the others."""
+    n = sh.n
+    X = np.linspace(0.0, 1.0, n + 1)
+    g = pkg.simplexgrid(X, X, X)
+    F = pkg.FESpace(pkg.H1P2(1, 3), g)
+    mesh = eng.mesh_set(g.coords, g.cellnodes, g.cellregions, g.cellvolumes)
+    sp = eng.space_set(mesh, F.fetype.fe_id, 1, F.celldofs, F.ndofs)
+    gpat = eng.pattern_build([sp])
+    eng.assemble_bilinear(gpat, eng.make_opdesc([(0, 1)], [(0, 1)], kernel_id=pkg.lib.kernel_id("standard"), factor=1.0))
+    eng.assemble_linear(gpat, eng.make_opdesc([(0, 0)], kernel_id=pkg.lib.kernel_id("sincos301"), params=[1.0]))
+    gnz, gb = eng.values_get(gpat)
+    gcp = eng.pattern_colptr(gpat)
+    lnz, lb = eng.values_get(pat)
+    gkeys = lattice_keys(F, n)
+    order = np.argsort(gkeys)
+    own = np.nonzero(sh.owned == 1)[0]
+    near = np.zeros(sh.FES.ndofs, bool)
+    for z in (sh.z0, sh.z1):
+        near |= np.abs(sh.kz - 2 * z) <= 4
+    rng = np.random.default_rng(sh.rank)
+    pick = np.unique(np.concatenate([own[near[own]], rng.choice(own, size=min(own.size, 100000), replace=False)]))
+    gcol = order[np.searchsorted(gkeys[order], sh.key[pick])]
+    worst, count = 0.0, 0
+    for c, gc in zip(pick, gcol):
+        a = gnz[gcp[gc] - 1:gcp[gc + 1] - 1]
+        b = lnz[colptr[c] - 1:colptr[c + 1] - 1]
+        assert a.size == b.size, "an owned column has a different length than in the single-GPU matrix"
+        worst = max(worst, float(np.abs(a - b).max()))
+        count += a.size
+    eb = float(np.abs(lb[pick] - gb[gcol]).max())
+    return {"matrix_max_rel": worst / float(np.abs(gnz).max()), "rhs_max_rel": eb / float(np.abs(gb).max()), "entries_checked": int(count),
+            "columns_checked": int(pick.size), "against": "the same mesh assembled on one GPU (no partition)"}
 
 
 def run_ours(args):
@@ -121,22 +181,25 @@ def run_ours(args):
         k, v = kv.split("=")
         eng.set_option(k.strip(), int(v))
     t0 = time.time()
-    grid, FES = build_problem(pkg, args.n, rank, world)
+    sh = build_problem(pkg, args.n, rank, world, args.scaling)
+    grid, FES = sh.grid, sh.FES
     t_mesh = time.time() - t0
     t0 = time.time()
-    mesh = eng.mesh_set(grid.coords, grid.cellnodes, grid.cellregions, grid.cellvolumes)
+    mesh = eng.mesh_set(grid.coords, grid.cellnodes, grid.cellregions, sh.cellvolumes)
     sp = eng.space_set(mesh, FES.fetype.fe_id, 1, FES.celldofs, FES.ndofs)
     pat = eng.pattern_build([sp])
     eng.synchronize()
     t_setup = time.time() - t0
     nrows, ncols, nnz = eng.pattern_dims(pat)
+    colptr = eng.pattern_colptr(pat) if (world == 1 or args.scaling == "strong") else None
     if world > 1:
-        # the slabs of neighbouring ranks share the dofs of one z-plane: interface-row contributions of the rhs are
-        # exchanged over NCCL inside every step (grouped send/recv, dist.cuh)
+        # owned-row form: after the local assembly the interface-row contributions of the matrix (whole column segments) and
+        # of the rhs go to the owning rank over NCCL (grouped send/recv, dist.cuh) inside every step
         uid = [pkg.lib.Engine.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.dist_init(rank, world, uid[0])
-        eng.dist_set_interfaces(pat, slab_interfaces(pkg, FES, rank, world))
+        plan = sh.owned_plan()
+        eng.dist_set_owned(pat, plan)
     lap = eng.make_opdesc([(0, 1)], [(0, 1)], kernel_id=pkg.lib.kernel_id("standard"), factor=1.0)
     rhs = eng.make_opdesc([(0, 0)], kernel_id=pkg.lib.kernel_id("sincos301"), params=[1.0])
 
@@ -144,7 +207,7 @@ def run_ours(args):
         eng.assemble_bilinear(pat, lap)
         eng.assemble_linear(pat, rhs)
         if world > 1:
-            eng.dist_sum_rhs(pat)
+            eng.dist_reduce_system(pat, True, True)
 
     def barrier():
         if world > 1:
@@ -174,27 +237,42 @@ def run_ours(args):
         if i == args.steps - 1:
             rhs_ms = np.array(eng.last_timings())
         if world > 1:
-            eng.dist_sum_rhs(pat)
+            eng.dist_reduce_system(pat, True, True)
     eng.event_record(1)
     ms_total = eng.event_elapsed_ms(0, 1)
     barrier()
     clocks = sampler.finish() if sampler else None
 
+    # ---- checks outside the timed region
+    parity = None
+    if world == 1 and not args.no_parity:
+        keys = lattice_keys(FES, args.n)
+        parity = parity_vs_oracle(pkg, eng, pat, args.n, args.n, keys, colptr, sorted({0, 1, args.n // 2, args.n}))
+    strong_check = None
+    if world > 1 and args.scaling == "strong" and not args.no_parity:
+        strong_check = parity_vs_single_gpu(pkg, eng, sh, pat, colptr)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, strong_check)
+        strong_check = {"matrix_max_rel": max(x["matrix_max_rel"] for x in gathered), "rhs_max_rel": max(x["rhs_max_rel"] for x in gathered),
+                        "entries_checked": sum(x["entries_checked"] for x in gathered), "columns_checked": sum(x["columns_checked"] for x in gathered),
+                        "against": gathered[0]["against"]}
+
     # ---- e2e through the C-ABI with HOST buffers: H2D of the coordinates (pinned), D2H of nzval and b
     coords_h = torch.from_numpy(np.ascontiguousarray(grid.coords)).pin_memory()
     nz_h = torch.empty(nnz, dtype=torch.float64).pin_memory()
     b_h = torch.empty(nrows, dtype=torch.float64).pin_memory()
-    vol_h = torch.from_numpy(np.ascontiguousarray(grid.cellvolumes)).pin_memory()
+    vol_h = torch.from_numpy(np.ascontiguousarray(sh.cellvolumes)).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
 
     def step_e2e():
         eng.mesh_update_coords(mesh, coords_h, vol_h)
-        eng.assemble_bilinear(pat, lap, nzval_out=nz_h)
         if world > 1:
+            eng.assemble_bilinear(pat, lap)
             eng.assemble_linear(pat, rhs)
-            eng.dist_sum_rhs(pat)
-            eng.values_get(pat, want_nzval=False, b_out=b_h)
+            eng.dist_reduce_system(pat, True, True)
+            eng.values_get(pat, nzval_out=nz_h, b_out=b_h)
         else:
+            eng.assemble_bilinear(pat, lap, nzval_out=nz_h)
             eng.assemble_linear(pat, rhs, b_out=b_h)
 
     step_e2e()
@@ -205,14 +283,15 @@ def run_ours(args):
     eng.event_record(3)
     ms_e2e = eng.event_elapsed_ms(2, 3) / e2e_steps
     barrier()
-    checksum = float(nz_h.sum())   # stiffness matrix annihilates constants: sum of all entries ~ 0
+    checksum = float(nz_h.sum())   # stiffness matrix annihilates constants: sum of all entries ~ 0 (single GPU)
 
     ms_step = ms_total / args.steps
     t = torch.tensor([ms_step, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step, ms_e2e = float(t[0]), float(t[1])
-    cells_total = grid.ncells * world
+    nz_layers = args.n * world if args.scaling == "weak" else args.n
+    cells_total = 6 * args.n * args.n * nz_layers
     value = cells_total / (ms_step * 1e-3)
     e2e_value = cells_total / (ms_e2e * 1e-3)
 
@@ -224,30 +303,34 @@ def run_ours(args):
         except Exception:
             pass
         peak = peaks.get("hbm_gbs", 6650.0)
-        alg = algorithmic_bytes(grid, FES, nnz)
-        traffic = None      # ncu dram__bytes_read.sum + dram__bytes_write.sum of the stiffness kernels (committed capture)
+        alg = algorithmic_bytes(3, FES.ndofs4cell, sh.ncells_owned, nnz)
+        traffic, traffic_src = None, None   # ncu dram__bytes_read.sum + dram__bytes_write.sum of the stiffness kernels (committed capture)
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_f_traffic.json")))
-            if tj.get("workload") == f"n={args.n}":
-                traffic = tj["stiffness_dram_bytes_per_assembly"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            if tj.get("workload") == f"n={args.n}" and world == 1:
+                traffic, traffic_src = tj["stiffness_dram_bytes_per_assembly"], tj.get("source")
         except Exception:
             pass
         dom_ms = kern_ms[0] + kern_ms[1]          # local + gather kernels of the stiffness assembly
         achieved = alg / (dom_ms * 1e-3) / 1e9
+        total_nnz = nnz * world if args.scaling == "weak" else None
+        wl = (f"Example301-like 3D H1P2 Poisson stiffness+RHS on structured simplexgrid n={args.n} "
+              f"({6 * args.n ** 3} tets, 13651919 dofs, 389543645 nnz at n=119)" if world == 1 or args.scaling == "strong" else
+              f"Example301-like 3D H1P2 Poisson stiffness+RHS, one n={args.n} slab ({6 * args.n ** 3} tets) per GPU of the stacked grid "
+              f"{args.n} x {args.n} x {args.n * world}")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"Example301-like 3D H1P2 Poisson stiffness+RHS on structured simplexgrid n={args.n} "
-                                   f"({grid.ncells} tets, {nrows} dofs, {nnz} nnz per GPU)",
-                       "l2_policy": "inputs+outputs (>= 4 GB per step) are larger than the 126 MB L2",
-                       "parallelism": (f"cell slabs x{world}; interface rows of the rhs exchanged over NCCL send/recv every step"
-                                       if world > 1 else "1 GPU")},
-            "nnz_per_s": nnz * world / (ms_step * 1e-3),
+            "config": {"workload": wl,
+                       "l2_policy": "inputs+outputs (>= 4 GB per step at n=119) are larger than the 126 MB L2",
+                       "parallelism": (f"z-slabs of whole cube layers x{world}, owned-row form: interface-row contributions of matrix and rhs "
+                                       f"reduced to the owning rank over NCCL send/recv every step" if world > 1 else "1 GPU")},
+            "nnz_per_s": (total_nnz or 389543645 * (args.n / 119.0) ** 3) / (ms_step * 1e-3) if world > 1 else nnz / (ms_step * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": "ncu capture profiles/r01_f_final_ncu_summary.txt" if traffic else None,
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "kernel": "stiffness assembly kernels (local + gather)", "kernel_ms": dom_ms,
+                         "kernel": "stiffness assembly kernels of rank 0 (geometry + owner-computes gather)", "kernel_ms": dom_ms,
                          "algorithmic_bytes": alg, "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(coords_h.numel() * 8 + vol_h.numel() * 8),
@@ -259,8 +342,14 @@ def run_ours(args):
             "phase_ms": {"stiffness_geo": kern_ms[0], "stiffness_gather": kern_ms[1], "rhs_cell": rhs_ms[0], "rhs_gather": rhs_ms[1]},
             "plan": eng.plan_stats(pat, 0),
         }
+        if parity is not None:
+            out["parity"] = parity
+        if strong_check is not None:
+            out["parity_vs_1gpu"] = strong_check
+        if world > 1:
+            out["local"] = {"cells_owned_rank0": sh.ncells_owned, "cells_with_ghost_layers_rank0": int(grid.ncells), "nnz_local_rank0": int(nnz)}
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(pkg, args)
+            out["cpu_baseline"] = cpu_baseline(pkg, args.cpu_n)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -268,30 +357,38 @@ def run_ours(args):
     return out
 
 
-def cpu_baseline(pkg, args, n_sample=None, steps=1, threads=None):
-    """The CPU restatement (oracle, a port of the reference's loops; Julia is not installed) timed on a bounded sample of
-    the same workload with all host threads: the sample grid is cut into one contiguous cell range per thread and every
-    thread assembles its range into its own matrix / vector (insertion into an existing CSC pattern) -- the scheme of the
+def cpu_baseline(pkg, n, steps=1, threads=None):
+    """The CPU restatement (oracle, a port of the reference's loops; Julia is not installed) timed on the operators of the
+    benchmark on simplexgrid n with all host threads: the grid is cut into one z-slab of cube layers per thread and every thread
+    assembles its slab into its own matrix / vector (insertion into an existing CSC pattern by binary search) -- the scheme of the
     reference's `parallel = true` path (thread-private parts per partition, bilinear_operator.jl:969-979)."""
     import threading
     from oracle import oracle as ora
     ora.build()
-    n = n_sample or args.cpu_n
-    T = threads or max(1, len(os.sched_getaffinity(0)))
+    T = min(threads or max(1, len(os.sched_getaffinity(0))), n)
+    h = 1.0 / n
     X = np.linspace(0, 1, n + 1)
-    grid = pkg.simplexgrid(X, X, X)
-    FES = pkg.FESpace(pkg.H1P2(1, 3), grid)
-    parts = []
-    for lo, hi in pkg.cell_ranges(grid.ncells, T):
-        sh = pkg.Shard(grid.coords, grid.cellnodes, grid.cellregions, FES.celldofs, lo, hi, order=2)
-        om = ora.Mesh(sh.coords, sh.cellnodes, sh.cellregions, np.ascontiguousarray(grid.cellvolumes[lo:hi]))
-        gr = ora.OraArg(sh.celldofs, 1, 2, ora.OP_GRAD)
-        idu = ora.OraArg(sh.celldofs, 1, 2, ora.OP_ID)
-        colptr, rowval = ora.structural_pattern([gr], [gr], (sh.ndofs, sh.ndofs))
-        parts.append((om, gr, idu, colptr, rowval, sh.ndofs))
+    parts = [None] * T
+    ncells = 0
+
+    def setup(i, z0, z1):
+        grid = pkg.simplexgrid(X, X, h * np.arange(z0, z1 + 1))
+        FES = pkg.FESpace(pkg.H1P2(1, 3), grid)
+        om = ora.Mesh(grid.coords, grid.cellnodes, grid.cellregions, grid.cellvolumes)
+        gr = ora.OraArg(FES.celldofs, 1, 2, ora.OP_GRAD)
+        idu = ora.OraArg(FES.celldofs, 1, 2, ora.OP_ID)
+        colptr, rowval = ora.structural_pattern([gr], [gr], (FES.ndofs, FES.ndofs))
+        parts[i] = (om, gr, idu, colptr, rowval, FES.ndofs, grid.ncells)
+
+    th = [threading.Thread(target=setup, args=(i, z0, z1)) for i, (z0, z1) in enumerate(pkg.layer_ranges(n, T))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    ncells = sum(p[6] for p in parts)
 
     def work(p):
-        om, gr, idu, colptr, rowval, nd = p
+        om, gr, idu, colptr, rowval, nd, _ = p
         ora.assemble_bilinear(om, [gr], [gr], "standard", csc=(colptr, rowval))
         b = np.zeros(nd)
         ora.assemble_linear(om, [idu], b, "sincos301", params=[1.0])
@@ -306,27 +403,28 @@ def cpu_baseline(pkg, args, n_sample=None, steps=1, threads=None):
             t.join()
         times.append(time.perf_counter() - t0)
     dt = float(np.mean(times))
-    return {"value": grid.ncells / dt, "unit": UNIT, "cores": T, "kind": "port",
-            "sample": f"same operators on simplexgrid n={n} ({grid.ncells} tets) cut into {T} cell ranges, one thread each, C "
+    return {"value": ncells / dt, "unit": UNIT, "cores": T, "kind": "port",
+            "sample": f"same operators on simplexgrid n={n} ({ncells} tets) cut into {T} z-slabs, one thread each (no NUMA pinning), C "
                       f"restatement of the reference loops (gcc -O2), {dt:.2f} s per step; the Julia reference is not installable offline",
             "seconds_per_step": dt}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path.  Julia and its three un-vendored dependencies are
-    not available offline, so this arm times the oracle port (kind 'port') on the host cores."""
+    """--impl reference: the reference's CPU path on the SAME configuration (n = 119 by default).  Julia and its three un-vendored
+    dependencies are not available offline, so this arm times the oracle port (kind 'port') with all host threads."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return None
     import __graft_entry__ as g
     pkg = g.load_package()
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_baseline(pkg, args, n_sample=8)
-    cb = cpu_baseline(pkg, args, steps=max(1, min(args.steps, 3)))
+    if args.warmup > 0:
+        cpu_baseline(pkg, 8)
+    cb = cpu_baseline(pkg, args.n, steps=max(1, min(args.steps, 2)))
     return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": env_int("WORLD_SIZE", 1),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Example301-like 3D H1P2 Poisson stiffness+RHS, bounded sample n={args.cpu_n}"},
+            "config": {"workload": f"Example301-like 3D H1P2 Poisson stiffness+RHS on structured simplexgrid n={args.n} "
+                                   f"({6 * args.n ** 3} tets, 13651919 dofs, 389543645 nnz at n=119)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
@@ -341,10 +439,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=119, help="cubes per axis (119 -> 10.1M tets, config 2)")
+    ap.add_argument("--n", "--grid-n", dest="n", type=int, default=119, help="cubes per axis (119 -> 10.1M tets, config 2)")
     ap.add_argument("--cpu-n", type=int, default=40, help="grid size of the bounded CPU sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size parity checks outside the timed region")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one n^3 slab per GPU (default), strong = ONE n^3 mesh partitioned over the GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     out = run_reference(args) if args.impl == "reference" else run_ours(args)

@@ -97,7 +97,8 @@ struct Pattern {
     int nchunks = 0;
     bool square = false;
     SolverWork cg;
-    IfacePlan iface;                           // partition interfaces (multi-GPU)
+    IfacePlan iface;                           // partition interfaces (multi-GPU, additive form)
+    OwnedPlanDev owned;                        // exchange lists of the owned-row form
 };
 
 struct TableKey {
@@ -2406,7 +2407,8 @@ int extfem_apply_penalties(extfem_ctx *ctx, int pattern, int64_t ndofs, const in
     if (int rc = ensure(C, err, 4)) return rc;
     EXTFEM_CUDA_CHECK(C, cudaMemsetAsync(err.p, 0, 4, C->stream));
     // sharded system: the diagonal lives on the owning rank only (additive form), b stays consistent
-    const double *owned = (C->dist.ready && C->dist.world > 1 && P.iface.ready) ? (const double *)P.iface.weight : nullptr;
+    const double *owned = nullptr;
+    if (C->dist.ready && C->dist.world > 1) owned = P.owned.ready ? (const double *)P.owned.weight : (P.iface.ready ? (const double *)P.iface.weight : nullptr);
     penalties_kernel<<<nblocks(ndofs, 256), 256, 0, C->stream>>>(ndofs, dd.as<long long>(), values ? dv.as<double>() : nullptr, penalty,
                                                                 P.colptr.as<long long>(), P.rowval.as<int>(), P.nzval.as<double>(),
                                                                 P.b.as<double>(), P.nrows, owned, err.as<int>());
@@ -2590,6 +2592,154 @@ int extfem_dist_cg(extfem_ctx *ctx, int pattern, const double *b, double *x, dou
     if (int rc = dist_jacobi_cg(C->stream, C->dist, P.iface, P.nrows, P.colptr.as<long long>(), P.rowval.as<int>(), P.nzval.as<double>(), bptr,
                                 dx.as<double>(), rtol, maxit, &it, &rr, P.cg, &C->launches, &e))
         return fail(C, rc == -5 ? EXTFEM_ERR_NCCL : EXTFEM_ERR_CUDA, "distributed CG failed, code " + std::to_string(rc) + " " + e);
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(x, dx.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    if (iters) *iters = it;
+    if (relres) *relres = rr;
+    return EXTFEM_OK;
+}
+
+/* ---- owned-row form (dist.cuh) ------------------------------------------------------------------------------------- */
+static int upload_rows(Ctx *C, long long nrows, const int64_t *ptr, const int64_t *rows, int nneigh, OwnedExchange &X, long long *count,
+                       void **dev, const char *what)
+{
+    std::vector<long long> &pp = (dev == &X.send_rows) ? X.send_ptr : X.recv_ptr;
+    pp.assign(1, 0);
+    for (int k = 0; k < nneigh; ++k) {
+        if (ptr[k + 1] < ptr[k]) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("extfem_dist_set_owned: bad pointer array of ") + what);
+        pp.push_back(ptr[k + 1] - ptr[0]);
+    }
+    const long long n = pp.back();
+    std::vector<int> r0((size_t)std::max(n, 1ll), 0);
+    for (long long i = 0; i < n; ++i) {
+        const long long r = rows[ptr[0] + i] - 1;
+        if (r < 0 || r >= nrows) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("extfem_dist_set_owned: row out of range in ") + what);
+        r0[i] = (int)r;
+    }
+    if (*dev) { cudaFree(*dev); *dev = nullptr; }
+    EXTFEM_CUDA_CHECK(C, cudaMalloc(dev, r0.size() * 4));
+    EXTFEM_CUDA_CHECK(C, cudaMemcpy(*dev, r0.data(), r0.size() * 4, cudaMemcpyHostToDevice));
+    *count = n;
+    return 0;
+}
+
+int extfem_dist_set_owned(extfem_ctx *ctx, int pattern, int nneigh, const int32_t *neigh_ranks, const int64_t *red_send_ptr,
+                          const int64_t *red_send_rows, const int64_t *red_recv_ptr, const int64_t *red_recv_rows,
+                          const int64_t *halo_send_ptr, const int64_t *halo_send_rows, const int64_t *halo_recv_ptr,
+                          const int64_t *halo_recv_rows, const uint8_t *owned)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (!C->dist.ready) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_init has not been called");
+    if (!P.square) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "the owned-row form needs a square system");
+    if (nneigh < 0 || !owned || (nneigh > 0 && (!neigh_ranks || !red_send_ptr || !red_recv_ptr || !halo_send_ptr || !halo_recv_ptr)))
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_set_owned: bad argument");
+    OwnedPlanDev &O = P.owned;
+    O.ready = false;
+    O.ranks.assign(neigh_ranks, neigh_ranks + nneigh);
+    for (int k = 0; k < nneigh; ++k)
+        if (neigh_ranks[k] < 0 || neigh_ranks[k] >= C->dist.world || neigh_ranks[k] == C->dist.rank)
+            return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_set_owned: bad neighbour list");
+    static const int64_t zero2[2] = {0, 0};
+    auto P0 = [&](const int64_t *p) { return nneigh > 0 ? p : zero2; };
+    if (int rc = upload_rows(C, P.nrows, P0(red_send_ptr), red_send_rows, nneigh, O.red, &O.red.nsend, &O.red.send_rows, "red_send")) return rc;
+    if (int rc = upload_rows(C, P.nrows, P0(red_recv_ptr), red_recv_rows, nneigh, O.red, &O.red.nrecv, &O.red.recv_rows, "red_recv")) return rc;
+    if (int rc = upload_rows(C, P.nrows, P0(halo_send_ptr), halo_send_rows, nneigh, O.halo, &O.halo.nsend, &O.halo.send_rows, "halo_send")) return rc;
+    if (int rc = upload_rows(C, P.nrows, P0(halo_recv_ptr), halo_recv_rows, nneigh, O.halo, &O.halo.nrecv, &O.halo.recv_rows, "halo_recv")) return rc;
+    // column segments of the matrix reduction
+    auto segs = [&](const std::vector<long long> &ptr, const int64_t *rows0, long long n, std::vector<long long> &seg, std::vector<long long> &vptr) {
+        seg.assign((size_t)n + 1, 0);
+        for (long long i = 0; i < n; ++i) { const long long c = rows0[i] - 1; seg[i + 1] = seg[i] + (P.hcolptr[c + 1] - P.hcolptr[c]); }
+        vptr.assign(ptr.size(), 0);
+        for (size_t k = 0; k < ptr.size(); ++k) vptr[k] = seg[ptr[k]];
+    };
+    std::vector<long long> sseg, rseg;
+    segs(O.red.send_ptr, red_send_rows ? red_send_rows + P0(red_send_ptr)[0] : nullptr, O.red.nsend, sseg, O.send_vptr);
+    segs(O.red.recv_ptr, red_recv_rows ? red_recv_rows + P0(red_recv_ptr)[0] : nullptr, O.red.nrecv, rseg, O.recv_vptr);
+    // the receive-side segment table is indexed per listed column (global offsets into recvbuf)
+    for (void **pp : {&O.send_seg, &O.recv_seg, &O.sendbuf, &O.recvbuf, &O.weight}) if (*pp) { cudaFree(*pp); *pp = nullptr; }
+    EXTFEM_CUDA_CHECK(C, cudaMalloc(&O.send_seg, sseg.size() * 8));
+    EXTFEM_CUDA_CHECK(C, cudaMalloc(&O.recv_seg, rseg.size() * 8));
+    EXTFEM_CUDA_CHECK(C, cudaMemcpy(O.send_seg, sseg.data(), sseg.size() * 8, cudaMemcpyHostToDevice));
+    EXTFEM_CUDA_CHECK(C, cudaMemcpy(O.recv_seg, rseg.data(), rseg.size() * 8, cudaMemcpyHostToDevice));
+    O.bufdoubles = (size_t)std::max<long long>({sseg.back(), rseg.back(), O.halo.nsend, O.halo.nrecv, O.red.nsend, O.red.nrecv, 1});
+    EXTFEM_CUDA_CHECK(C, cudaMalloc(&O.sendbuf, O.bufdoubles * 8));
+    EXTFEM_CUDA_CHECK(C, cudaMalloc(&O.recvbuf, O.bufdoubles * 8));
+    std::vector<double> w((size_t)P.nrows);
+    for (long long i = 0; i < P.nrows; ++i) w[i] = owned[i] ? 1.0 : 0.0;
+    EXTFEM_CUDA_CHECK(C, cudaMalloc(&O.weight, w.size() * 8));
+    EXTFEM_CUDA_CHECK(C, cudaMemcpy(O.weight, w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+    // both sides of every exchange must agree on the column lengths (same rows in the same order): exchange and compare
+    if (C->dist.world > 1 && (O.red.nsend > 0 || O.red.nrecv > 0)) {
+        std::vector<double> mylen((size_t)std::max(O.red.nsend, 1ll)), got((size_t)std::max(O.red.nrecv, 1ll));
+        for (long long i = 0; i < O.red.nsend; ++i) mylen[i] = (double)(sseg[i + 1] - sseg[i]);
+        EXTFEM_CUDA_CHECK(C, cudaMemcpy(O.sendbuf, mylen.data(), (size_t)O.red.nsend * 8, cudaMemcpyHostToDevice));
+        std::string e;
+        if (owned_sendrecv(C->stream, C->dist, O.ranks, O.red.send_ptr, O.red.recv_ptr, (const double *)O.sendbuf, (double *)O.recvbuf, &e))
+            return fail(C, EXTFEM_ERR_NCCL, e);
+        EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+        EXTFEM_CUDA_CHECK(C, cudaMemcpy(got.data(), O.recvbuf, (size_t)O.red.nrecv * 8, cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < O.red.nrecv; ++i)
+            if ((long long)got[i] != rseg[i + 1] - rseg[i])
+                return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_set_owned: a shared column has different lengths on the two ranks "
+                                                        "(the local meshes need one layer of ghost cells, host/dist.py: OwnedShard)");
+    }
+    O.ready = true;
+    return EXTFEM_OK;
+}
+
+#define GET_OWNED()                                                                                    \
+    if (!C->dist.ready || !P.owned.ready)                                                              \
+        return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "extfem_dist_init / extfem_dist_set_owned have not been called");
+
+int extfem_dist_reduce_system(extfem_ctx *ctx, int pattern, int matrix, int rhs)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    GET_OWNED();
+    std::string e;
+    if (matrix && owned_reduce_matrix(C->stream, C->dist, P.owned, P.colptr.as<long long>(), P.nzval.as<double>(), &C->launches, &e))
+        return fail(C, EXTFEM_ERR_NCCL, e.empty() ? "matrix reduction failed" : e);
+    if (rhs && owned_reduce_vector(C->stream, C->dist, P.owned, P.b.as<double>(), &C->launches, &e))
+        return fail(C, EXTFEM_ERR_NCCL, e.empty() ? "rhs reduction failed" : e);
+    return EXTFEM_OK;
+}
+
+int extfem_dist_spmv_owned(extfem_ctx *ctx, int pattern, const double *x, double *y)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    GET_OWNED();
+    if (!x || !y) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "x or y is NULL");
+    DevBuf dx, dy;
+    if (int rc = upload(C, dx, x, (size_t)P.ncols * 8)) return rc;
+    if (int rc = ensure(C, dy, (size_t)P.nrows * 8)) return rc;
+    std::string e;
+    if (owned_halo(C->stream, C->dist, P.owned, dx.as<double>(), &C->launches, &e)) return fail(C, EXTFEM_ERR_NCCL, e.empty() ? "halo exchange failed" : e);
+    spmv_kernel<<<nblocks(P.nrows * SPMV_LANES, 256), 256, 0, C->stream>>>(P.nrows, P.colptr.as<long long>(), P.rowval.as<int>(), nullptr,
+                                                                           P.nzval.as<double>(), dx.as<double>(), dy.as<double>());
+    mask_rows_kernel<<<nblocks(P.nrows, 256), 256, 0, C->stream>>>(P.nrows, (const double *)P.owned.weight, dy.as<double>());
+    LAUNCHED(C); LAUNCHED(C);
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(y, dy.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    return EXTFEM_OK;
+}
+
+int extfem_dist_cg_owned(extfem_ctx *ctx, int pattern, const double *b, double *x, double rtol, int maxit, int *iters, double *relres)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    GET_OWNED();
+    if (!x) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "x is NULL");
+    DevBuf db, dx;
+    const double *bptr = P.b.as<double>();
+    if (b) { if (int rc = upload(C, db, b, (size_t)P.nrows * 8)) return rc; bptr = db.as<double>(); }
+    if (int rc = upload(C, dx, x, (size_t)P.nrows * 8)) return rc;
+    int it = 0; double rr = 0;
+    std::string e;
+    if (int rc = owned_jacobi_cg(C->stream, C->dist, P.owned, P.nrows, P.colptr.as<long long>(), P.rowval.as<int>(), P.nzval.as<double>(), bptr,
+                                 dx.as<double>(), rtol, maxit, &it, &rr, P.cg, &C->launches, &e))
+        return fail(C, rc == -5 ? EXTFEM_ERR_NCCL : EXTFEM_ERR_CUDA, "owned-row CG failed, code " + std::to_string(rc) + " " + e);
     EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(x, dx.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
     EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
     if (iters) *iters = it;

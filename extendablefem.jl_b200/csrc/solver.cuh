@@ -241,7 +241,9 @@ static inline int jacobi_cg(cudaStream_t st, long long n, long long nnz, const l
     dot(r, r, 5, 0);
     double h[8];
     if (cudaMemcpyAsync(h, sc, 64, cudaMemcpyDeviceToHost, st) || cudaStreamSynchronize(st)) return -2;
-    double bnorm = std::sqrt(h[6]);
+    // the residual is measured against the INITIAL residual |b - A x0| (== |b| for x0 = 0): with penalised Dirichlet rows
+    // (1e30 * value) in b, |b| would hide the interior residual; callers pass x0 with the boundary values set
+    double bnorm = std::sqrt(h[5]);
     if (bnorm == 0.0) bnorm = 1.0;
     double res = std::sqrt(h[5]) / bnorm;
     int it = 0;

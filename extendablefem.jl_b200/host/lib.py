@@ -27,6 +27,7 @@ EXPORTS = [
     "extfem_apply_penalties", "extfem_residual", "extfem_spmv", "extfem_cg", "extfem_plan_stats", "extfem_plan_jit_status",
     "extfem_dist_unique_id", "extfem_dist_init", "extfem_dist_set_interfaces", "extfem_dist_sum_rhs", "extfem_dist_spmv", "extfem_dist_cg",
     "extfem_mesh_set_bfaces", "extfem_space_set_bfacedofs", "extfem_integrate", "extfem_values_zero", "extfem_apply_values",
+    "extfem_dist_set_owned", "extfem_dist_reduce_system", "extfem_dist_spmv_owned", "extfem_dist_cg_owned",
 ]
 
 
@@ -188,6 +189,13 @@ class Engine:
         rowval = np.empty(nnz, np.int64)
         self._check(self.lib.extfem_pattern_get(self.ctx, pattern, _p(colptr), _p(rowval)))
         return colptr, rowval
+
+    def pattern_colptr(self, pattern: int):
+        """colptr only (Int64, 1-based): the row indices of a 10M-cell pattern are 3 GB"""
+        _, ncols, _ = self.pattern_dims(pattern)
+        colptr = np.empty(ncols + 1, np.int64)
+        self._check(self.lib.extfem_pattern_get(self.ctx, pattern, _p(colptr), None))
+        return colptr
 
     # ---- operators -------------------------------------------------------------------------------
     def make_opdesc(self, test, ansatz=(), args=(), kernel_id=1, params=(), factor=1.0, time=0.0, quadorder=-1,
@@ -373,6 +381,32 @@ class Engine:
         bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
         it, rr = C.c_int(), C.c_double()
         self._check(self.lib.extfem_dist_cg(self.ctx, pattern, _p(bb), _p(x), C.c_double(rtol), int(maxit), C.byref(it), C.byref(rr)))
+        return x, it.value, rr.value
+
+    # owned-row form
+    def dist_set_owned(self, pattern: int, plan):
+        a = lambda v, t: np.ascontiguousarray(v, dtype=t)      # noqa: E731
+        arrs = [a(plan.neigh, np.int32), a(plan.red_send_ptr, np.int64), a(plan.red_send, np.int64), a(plan.red_recv_ptr, np.int64),
+                a(plan.red_recv, np.int64), a(plan.halo_send_ptr, np.int64), a(plan.halo_send, np.int64), a(plan.halo_recv_ptr, np.int64),
+                a(plan.halo_recv, np.int64), a(plan.owned, np.uint8)]
+        self._check(self.lib.extfem_dist_set_owned(self.ctx, pattern, int(arrs[0].size), *[_p(x) for x in arrs]))
+
+    def dist_reduce_system(self, pattern: int, matrix=True, rhs=True):
+        self._check(self.lib.extfem_dist_reduce_system(self.ctx, pattern, int(matrix), int(rhs)))
+
+    def dist_spmv_owned(self, pattern, x):
+        nrows, _, _ = self.pattern_dims(pattern)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(nrows)
+        self._check(self.lib.extfem_dist_spmv_owned(self.ctx, pattern, _p(x), _p(y)))
+        return y
+
+    def dist_cg_owned(self, pattern, b=None, x0=None, rtol=1e-10, maxit=10000):
+        nrows, _, _ = self.pattern_dims(pattern)
+        x = np.zeros(nrows) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        it, rr = C.c_int(), C.c_double()
+        self._check(self.lib.extfem_dist_cg_owned(self.ctx, pattern, _p(bb), _p(x), C.c_double(rtol), int(maxit), C.byref(it), C.byref(rr)))
         return x, it.value, rr.value
 
     def launch_count(self) -> int:

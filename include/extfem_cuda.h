@@ -248,7 +248,8 @@ int extfem_residual(extfem_ctx *ctx, int pattern, const double *sol, double *res
 /* y = A*x on the device-resident matrix */
 int extfem_spmv(extfem_ctx *ctx, int pattern, const double *x, double *y);
 /* Jacobi-preconditioned CG on the device-resident system (square patterns); b == NULL uses the
- * device-resident right-hand side.  x is in/out (initial guess).  The matrix must be SYMMETRIC positive definite: the CSC
+ * device-resident right-hand side.  x is in/out (initial guess); the iteration stops when |b - A x| <= rtol * |b - A x0| (pass x0
+ * with the Dirichlet values set when rows are penalised).  The matrix must be SYMMETRIC positive definite: the CSC
  * arrays are traversed as CSR (A^T x); use extfem_spmv / extfem_residual (which build a true row-major view) for
  * non-symmetric systems such as Newton matrices of convection terms.                           */
 int extfem_cg(extfem_ctx *ctx, int pattern, const double *b, double *x, double rtol, int maxit, int *iters,
@@ -273,6 +274,27 @@ int extfem_dist_spmv(extfem_ctx *ctx, int pattern, const double *x, double *y);
 /* Jacobi-preconditioned CG on the sharded system; b == NULL uses the (consistent) device-resident rhs */
 int extfem_dist_cg(extfem_ctx *ctx, int pattern, const double *b, double *x, double rtol, int maxit, int *iters,
                    double *relres);
+
+/* ---- owned-row form (north_star: "owned-row assembly ... NCCL exchanges only interface-row contributions"): every dof has ONE
+ *      owner rank; the local mesh of a rank carries one layer of zero-volume ghost cells (host/dist.py: OwnedShard), so the
+ *      column of a shared dof has the same rows, in the same order, on every rank that holds it.  After the local assemble calls,
+ *      extfem_dist_reduce_system sends the non-owners' column segments (matrix) and rows (rhs) of shared dofs to the owner, which
+ *      adds them: the owner holds the complete, merged rows -- what flush! produces from the partitions in the reference
+ *      (bilinear_operator.jl:969-993).  Rows are per neighbour in an order both sides agree on (ascending global dof id):
+ *        red_send   my NON-owned rows that receive contributions of my own cells   -> their owner
+ *        red_recv   my owned rows the neighbour contributes to
+ *        halo_send  my owned rows of which the neighbour holds a copy (for SpMV)   / halo_recv  my copies of the neighbour's rows */
+int extfem_dist_set_owned(extfem_ctx *ctx, int pattern, int nneigh, const int32_t *neigh_ranks, const int64_t *red_send_ptr,
+                          const int64_t *red_send_rows, const int64_t *red_recv_ptr, const int64_t *red_recv_rows,
+                          const int64_t *halo_send_ptr, const int64_t *halo_send_rows, const int64_t *halo_recv_ptr,
+                          const int64_t *halo_recv_rows, const uint8_t *owned /*[nrows]*/);
+/* interface contributions of the device-resident matrix (column segments) and / or rhs to their owners */
+int extfem_dist_reduce_system(extfem_ctx *ctx, int pattern, int matrix, int rhs);
+/* y = A x on owned rows (0 elsewhere) after a halo exchange of x; symmetric matrices (the CSC arrays are traversed as CSR) */
+int extfem_dist_spmv_owned(extfem_ctx *ctx, int pattern, const double *x, double *y);
+/* Jacobi-preconditioned CG on the owned-row system (SPD); b == NULL: device-resident rhs; x comes back consistent on all local dofs */
+int extfem_dist_cg_owned(extfem_ctx *ctx, int pattern, const double *b, double *x, double rtol, int maxit, int *iters,
+                         double *relres);
 
 #ifdef __cplusplus
 }
