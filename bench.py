@@ -70,6 +70,30 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa(local_rank):
+    """Best effort: run this rank (and allocate its pinned staging buffers) on the CPU cores next to its GPU, so that the
+    end-to-end copies of several ranks do not cross the socket interconnect (`nvidia-smi topo -m`, column CPU Affinity)."""
+    import re
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        for line in out.splitlines():
+            tok = line.split()
+            if tok and tok[0] == f"GPU{local_rank}":
+                for t in tok[1:]:
+                    if re.fullmatch(r"\d+-\d+(,\d+-\d+)*", t):
+                        cpus = set()
+                        for part in t.split(","):
+                            a, b = part.split("-")
+                            cpus.update(range(int(a), int(b) + 1))
+                        cpus &= os.sched_getaffinity(0)
+                        if cpus:
+                            os.sched_setaffinity(0, cpus)
+                            return sorted(cpus)[0], len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def build_problem(pkg, n, rank=0, world=1, scaling="weak"):
     """Structured grid simplexgrid(0:1/n:1, 0:1/n:1, 0:1/n:nz/n) (6 tets per cube) cut into z-slabs of whole cube layers, one per
     rank.  weak: nz = n * world (every rank owns an n^3-cube slab); strong: nz = n (ONE n^3 mesh shared by all ranks).  With
@@ -176,6 +200,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else None
     eng = pkg.lib.Engine(local_rank)
     for kv in filter(None, os.environ.get("EXTFEM_OPTIONS", "").split(",")):   # tuning knobs, e.g. template_pool_bytes=57344
         k, v = kv.split("=")
@@ -205,9 +230,11 @@ def run_ours(args):
 
     def step_resident():
         eng.assemble_bilinear(pat, lap)
+        if world > 1:
+            eng.dist_reduce_system(pat, True, False)      # matrix interface rows: on the exchange stream, beside the rhs assembly
         eng.assemble_linear(pat, rhs)
         if world > 1:
-            eng.dist_reduce_system(pat, True, True)
+            eng.dist_reduce_system(pat, False, True)
 
     def barrier():
         if world > 1:
@@ -233,11 +260,13 @@ def run_ours(args):
         eng.assemble_bilinear(pat, lap)
         if i == args.steps - 1:
             kern_ms = np.array(eng.last_timings())
+        if world > 1:
+            eng.dist_reduce_system(pat, True, False)
         eng.assemble_linear(pat, rhs)
         if i == args.steps - 1:
             rhs_ms = np.array(eng.last_timings())
         if world > 1:
-            eng.dist_reduce_system(pat, True, True)
+            eng.dist_reduce_system(pat, False, True)
     eng.event_record(1)
     ms_total = eng.event_elapsed_ms(0, 1)
     barrier()
@@ -268,8 +297,9 @@ def run_ours(args):
         eng.mesh_update_coords(mesh, coords_h, vol_h)
         if world > 1:
             eng.assemble_bilinear(pat, lap)
+            eng.dist_reduce_system(pat, True, False)
             eng.assemble_linear(pat, rhs)
-            eng.dist_reduce_system(pat, True, True)
+            eng.dist_reduce_system(pat, False, True)
             eng.values_get(pat, nzval_out=nz_h, b_out=b_h)
         else:
             eng.assemble_bilinear(pat, lap, nzval_out=nz_h)
@@ -347,6 +377,7 @@ def run_ours(args):
         if strong_check is not None:
             out["parity_vs_1gpu"] = strong_check
         if world > 1:
+            out["cpu_binding_rank0"] = numa
             out["local"] = {"cells_owned_rank0": sh.ncells_owned, "cells_with_ghost_layers_rank0": int(grid.ncells), "nnz_local_rank0": int(nnz)}
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(pkg, args.cpu_n)

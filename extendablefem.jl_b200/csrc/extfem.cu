@@ -143,6 +143,9 @@ struct Ctx {
     int tmpl_classmask = 3;     // option "template_class_mask": tuning aid (time the short- / long-column warps alone)
     bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator
     long long launches = 0;
+    cudaStream_t stream2 = nullptr;   // exchange stream: the interface reduction of the matrix runs beside the rhs assembly
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool aux_pending = false;         // work on stream2 that later calls on the main stream must wait for
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t uev[16] = {};
     double last_ms[3] = {0, 0, 0};
@@ -1648,10 +1651,18 @@ static int assemble_bfaces(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
 
 using namespace extfem;
 
-#define CTX_GUARD(ctx)                                                                  \
+// work queued on the exchange stream is ordered before anything a later call puts on the main stream (every entry point except
+// extfem_assemble_linear, which touches neither the matrix values nor the exchange buffers)
+static inline void join_aux(Ctx *C)
+{
+    if (C->aux_pending) { cudaStreamWaitEvent(C->stream, C->ev_join, 0); C->aux_pending = false; }
+}
+
+#define CTX_GUARD_NOJOIN(ctx)                                                           \
     if (!(ctx)) { set_error(nullptr, EXTFEM_ERR_BAD_ARGUMENT, "ctx is NULL"); return EXTFEM_ERR_BAD_ARGUMENT; } \
     Ctx *C = reinterpret_cast<Ctx *>(ctx);                                              \
     cudaSetDevice(C->device);
+#define CTX_GUARD(ctx) CTX_GUARD_NOJOIN(ctx) join_aux(C);
 
 #define GET_PATTERN(id)                                                                 \
     if ((id) < 0 || (id) >= (int)C->patterns.size() || !C->patterns[id])                \
@@ -1677,6 +1688,9 @@ int extfem_ctx_create(int device, extfem_ctx **out)
     }
     for (auto &ev : C->ev) cudaEventCreate(&ev);
     for (auto &ev : C->uev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&C->stream2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&C->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&C->ev_join, cudaEventDisableTiming);
     if (const char *e = getenv("EXTFEM_DISABLE_FASTPATH")) C->fast_enabled = !(e[0] == '1');
     *out = reinterpret_cast<extfem_ctx *>(C);
     return EXTFEM_OK;
@@ -1690,6 +1704,9 @@ int extfem_ctx_destroy(extfem_ctx *ctx)
     cudaStreamSynchronize(C->stream);
     for (auto &ev : C->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : C->uev) if (ev) cudaEventDestroy(ev);
+    if (C->stream2) { cudaStreamSynchronize(C->stream2); cudaStreamDestroy(C->stream2); }
+    if (C->ev_fork) cudaEventDestroy(C->ev_fork);
+    if (C->ev_join) cudaEventDestroy(C->ev_join);
     C->patterns.clear(); C->spaces.clear(); C->meshes.clear();
     g_const_tmpl_owner[C->device % EXTFEM_MAXDEV] = nullptr;   // plans of this context may have owned the constant banks
     g_planemask_owner[C->device % EXTFEM_MAXDEV] = nullptr;
@@ -2136,7 +2153,7 @@ int extfem_assemble_bilinear(extfem_ctx *ctx, int pattern, const extfem_opdesc *
 
 int extfem_assemble_linear(extfem_ctx *ctx, int pattern, const extfem_opdesc *d, const double *sol, int accumulate, double *b_out)
 {
-    CTX_GUARD(ctx);
+    CTX_GUARD_NOJOIN(ctx);
     GET_PATTERN(pattern);
     Prepared R;
     if (int rc = prepare(C, P, d, KIND_LINEAR, d && d->nargs > 0 ? sol : nullptr, R)) return rc;
@@ -2698,10 +2715,20 @@ int extfem_dist_reduce_system(extfem_ctx *ctx, int pattern, int matrix, int rhs)
     GET_PATTERN(pattern);
     GET_OWNED();
     std::string e;
-    if (matrix && owned_reduce_matrix(C->stream, C->dist, P.owned, P.colptr.as<long long>(), P.nzval.as<double>(), &C->launches, &e))
-        return fail(C, EXTFEM_ERR_NCCL, e.empty() ? "matrix reduction failed" : e);
-    if (rhs && owned_reduce_vector(C->stream, C->dist, P.owned, P.b.as<double>(), &C->launches, &e))
-        return fail(C, EXTFEM_ERR_NCCL, e.empty() ? "rhs reduction failed" : e);
+    if (matrix) {
+        // on the exchange stream, behind everything queued so far: a following extfem_assemble_linear overlaps with it
+        EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev_fork, C->stream));
+        EXTFEM_CUDA_CHECK(C, cudaStreamWaitEvent(C->stream2, C->ev_fork, 0));
+        if (owned_reduce_matrix(C->stream2, C->dist, P.owned, P.colptr.as<long long>(), P.nzval.as<double>(), &C->launches, &e))
+            return fail(C, EXTFEM_ERR_NCCL, e.empty() ? "matrix reduction failed" : e);
+        EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev_join, C->stream2));
+        C->aux_pending = true;
+    }
+    if (rhs) {
+        join_aux(C);   // the exchange buffers are shared
+        if (owned_reduce_vector(C->stream, C->dist, P.owned, P.b.as<double>(), &C->launches, &e))
+            return fail(C, EXTFEM_ERR_NCCL, e.empty() ? "rhs reduction failed" : e);
+    }
     return EXTFEM_OK;
 }
 

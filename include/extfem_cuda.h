@@ -288,7 +288,9 @@ int extfem_dist_set_owned(extfem_ctx *ctx, int pattern, int nneigh, const int32_
                           const int64_t *red_send_rows, const int64_t *red_recv_ptr, const int64_t *red_recv_rows,
                           const int64_t *halo_send_ptr, const int64_t *halo_send_rows, const int64_t *halo_recv_ptr,
                           const int64_t *halo_recv_rows, const uint8_t *owned /*[nrows]*/);
-/* interface contributions of the device-resident matrix (column segments) and / or rhs to their owners */
+/* interface contributions of the device-resident matrix (column segments) and / or rhs to their owners.  The matrix reduction
+ * runs on the context's exchange stream: an extfem_assemble_linear issued next overlaps with it; every other call (and
+ * extfem_synchronize) is ordered behind it.                                                                            */
 int extfem_dist_reduce_system(extfem_ctx *ctx, int pattern, int matrix, int rhs);
 /* y = A x on owned rows (0 elsewhere) after a halo exchange of x; symmetric matrices (the CSC arrays are traversed as CSR) */
 int extfem_dist_spmv_owned(extfem_ctx *ctx, int pattern, const double *x, double *y);
