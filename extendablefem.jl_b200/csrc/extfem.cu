@@ -128,8 +128,10 @@ struct Ctx {
     DevBuf custom_qw, custom_qx;
     DevBuf loc, bloc, sol, params_scratch, tab, geo, visit, fq;
     bool fast_enabled = true;   // option "fastpath"
-    int nl_version = 3;         // option "nonlinear_kernel": 1 entry-wise local kernel, 2 staged per block, 3 warp per cell
+    int nl_version = 4;         // option "nonlinear_kernel": 1 entry-wise local kernel, 2 staged per block, 3 warp per cell,
+                                // 4 warp per cell with the contractions on FP64 tensor cores (falls back to 3 when not applicable)
     DevBuf nl2buf;
+    DevBuf nlpt;                // w J and (J u - F) per (cell, quadrature point) of the tensor-core nonlinear path
     bool tmpl_enabled = true;   // option "fastpath_templates": 0 keeps every column on the record kernel
     int tmpl_ahead = 1024;      // option "template_prefetch_ctas": CTAs ahead whose start-up data is prefetched into L2
     int tmpl_pool = TP_POOL_BYTES; // option "template_pool_bytes": shared-memory pool of one template CTA
@@ -1366,7 +1368,7 @@ static bool nl3_dofops(const ArgDev *args, int nargs, int dim, double offdiag, i
     return n <= CVC_MAX;
 }
 
-static int build_nl3_tables(Ctx *ctx, const OpDev &op, NL3Tables &T, bool *ok)
+static int build_nl3_tables(Ctx *ctx, const OpDev &op, NL3Tables &T, bool *ok, bool want_dense = false)
 {
     *ok = false;
     memset(&T, 0, sizeof(T));
@@ -1416,12 +1418,32 @@ static int build_nl3_tables(Ctx *ctx, const OpDev &op, NL3Tables &T, bool *ok)
     };
     T.NC = op.NC; T.NR = op.NR; T.same = same ? 1 : 0;
     pack(cols, op.NC, T.EC, T.o_cn, T.o_cout, T.o_bgidx, T.o_bgsc);
+    {   // dense operator matrix of the tensor-core kernel (kernels_generic.cuh: local_nonlinear_kernel4)
+        T.NT4 = (std::max(op.NC, op.NR) + 7) / 8;
+        T.Np4 = T.NT4 <= 2 ? 20 : 36;
+        T.dense_ok = same && op.nin == op.nout && op.nin <= 16 && T.NT4 <= 4 && nl4_warp_doubles(op.nq, op.nin, op.nout, T.Np4, off) * 8 * 4 <= 120 * 1024;
+        T.o_pt = reserve((size_t)T.EC * op.NC * 4);
+        for (int x = 0; x < T.EC; ++x)
+            for (int j = 0; j < op.NC; ++j) {
+                unsigned char *e = host.data() + T.o_pt + ((size_t)x * op.NC + j) * 4;
+                const bool live = x < cols[j].n;
+                e[0] = live ? (unsigned char)cols[j].space : 0; e[1] = live ? (unsigned char)cols[j].scalar : 0;
+                e[2] = live ? (unsigned char)cols[j].src[x] : 0; e[3] = 0;
+            }
+        T.o_ddst = reserve((size_t)T.EC * op.NC * 2);
+        for (int x = 0; x < T.EC; ++x)
+            for (int j = 0; j < op.NC; ++j)
+                reinterpret_cast<unsigned short *>(host.data() + T.o_ddst)[(size_t)x * op.NC + j] =
+                    (unsigned short)((T.dense_ok && x < cols[j].n ? cols[j].out[x] : 0) * T.Np4 + j);
+    }
     if (same) { T.ER = T.EC; T.o_rn = T.o_cn; T.o_rout = T.o_cout; T.o_btidx = T.o_bgidx; T.o_btsc = T.o_bgsc; }
     else pack(rows, op.NR, T.ER, T.o_rn, T.o_rout, T.o_btidx, T.o_btsc);
     if ((size_t)op.nq * op.nin * op.nout >= 65536 || (size_t)op.nq * T.EC * op.NC >= 65536 || (size_t)op.nq * T.ER * op.NR >= 65536 ||
         (size_t)op.nq * op.NC * op.nout >= 65536)
         return 0;   // 16-bit offsets
     const std::vector<NL3Dof> &rws = same ? cols : rows;
+    const bool skip_sparse = want_dense && T.dense_ok;   // the tensor-core kernel needs only the B tables and their dense places
+    if (!skip_sparse) {
     T.o_gjj = reserve((size_t)op.nq * op.NC * op.nout * T.EC * 2);
     T.o_gjb = reserve((size_t)op.nq * op.NC * op.nout * T.EC * 2);
     {
@@ -1446,6 +1468,7 @@ static int build_nl3_tables(Ctx *ctx, const OpDev &op, NL3Tables &T, bool *ok)
                 reinterpret_cast<unsigned short *>(host.data() + T.o_enb)[i] = (unsigned short)(x * op.NR + k);
                 reinterpret_cast<unsigned short *>(host.data() + T.o_eng)[i] = (unsigned short)(j * op.nout + (live ? rws[k].out[x] : 0));
             }
+    }
     {
         std::vector<unsigned short> uptr(op.nin + 1, 0), ulist;
         for (int o = 0; o < op.nin; ++o) {
@@ -1693,6 +1716,18 @@ int extfem_ctx_create(int device, extfem_ctx **out)
     cudaEventCreateWithFlags(&C->ev_join, cudaEventDisableTiming);
     if (const char *e = getenv("EXTFEM_DISABLE_FASTPATH")) C->fast_enabled = !(e[0] == '1');
     *out = reinterpret_cast<extfem_ctx *>(C);
+    if (const char *e = getenv("EXTFEM_OPTIONS")) {   // tuning knobs for every context of the process: "key=value,key=value"
+        std::string all(e);
+        size_t i = 0;
+        while (i < all.size()) {
+            size_t j = all.find(',', i);
+            if (j == std::string::npos) j = all.size();
+            const std::string kv = all.substr(i, j - i);
+            const size_t q = kv.find('=');
+            if (q != std::string::npos) extfem_set_option(*out, kv.substr(0, q).c_str(), atoi(kv.c_str() + q + 1));
+            i = j + 1;
+        }
+    }
     return EXTFEM_OK;
 }
 
@@ -1755,7 +1790,7 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "fastpath")) { C->fast_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_closed_form")) { C->bary_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_v2")) { C->nl_version = value != 0 ? 3 : 1; return EXTFEM_OK; }
-    if (key && !strcmp(key, "nonlinear_kernel")) { C->nl_version = std::min(std::max(value, 1), 3); return EXTFEM_OK; }
+    if (key && !strcmp(key, "nonlinear_kernel")) { C->nl_version = std::min(std::max(value, 1), 4); return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_prefetch_ctas")) { C->tmpl_ahead = value < 0 ? 0 : value; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_pool_bytes")) { C->tmpl_pool = std::min(std::max(value, 4096), 200 * 1024); return EXTFEM_OK; }
@@ -2237,10 +2272,41 @@ int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc 
     const bool v2 = C->nl_version >= 2 && cv_entries(op.args, op.nargs) <= CVC_MAX && cv_entries(op.test, op.ntest) <= CVC_MAX && op.nin + op.nout <= 255;
     NL3Tables T3;
     bool v3 = false;
-    if (C->nl_version >= 3) if (int rc = build_nl3_tables(C, op, T3, &v3)) return rc;
+    // the tensor-core path evaluates the kernel per (cell, point) with its vectors in registers: instantiated input lengths
+    const bool nl4_points_ok = op.nin == op.nout && (op.nin == 2 || op.nin == 3 || op.nin == 4 || op.nin == 7 || op.nin == 9);
+    if (C->nl_version >= 4 && nl4_points_ok)
+        if (int rc = ensure(C, C->nlpt, (size_t)op.ncells * op.nq * (op.nin * op.nout + op.nout) * 8)) return rc;
+    if (C->nl_version >= 3) if (int rc = build_nl3_tables(C, op, T3, &v3, C->nl_version >= 4 && nl4_points_ok)) return rc;
     int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
         constexpr int DIM = decltype(dimc)::value;
-        if (v3) {
+        if (v3 && C->nl_version >= 4 && T3.dense_ok && nl4_points_ok) {
+            const size_t wd = nl4_warp_doubles(op.nq, op.nin, op.nout, T3.Np4, T3.phi_off[T3.nspaces]);
+            const int nw = 4, cpw = 8;
+            const size_t smem = (size_t)nw * wd * 8 + T3.tab_bytes;
+            if (smem <= 220 * 1024) {
+                const long long ntot = op.ncells * op.nq;
+                double *wJ = C->nlpt.as<double>(), *rqg = wJ + (size_t)ntot * op.nin * op.nout;
+                // (1) kernel value and Jacobian per (cell, point), one thread each
+                const unsigned gp = nblocks(ntot, 128);
+                switch (op.nin) {
+#define EXTFEM_NLPT(N) case N: smem_attr(C, (const void *)nl_point_kernel<DIM, N>, 200 * 1024); \
+                       nl_point_kernel<DIM, N><<<gp, 128, T3.tab_bytes + (size_t)(128 / op.nq + 2) * op.NC * 8, C->stream>>>(op, T3, wJ, rqg); break;
+                EXTFEM_NLPT(2) EXTFEM_NLPT(3) EXTFEM_NLPT(4) EXTFEM_NLPT(7) EXTFEM_NLPT(9)
+#undef EXTFEM_NLPT
+                }
+                ++C->launches;
+                // (2) contractions on the FP64 tensor cores, one warp per cell
+                const unsigned gb = nblocks(op.ncells, nw * cpw);
+                switch (T3.NT4) {
+#define EXTFEM_NL4(N) case N: smem_attr(C, (const void *)local_nonlinear_kernel4<DIM, N>, 227 * 1024); \
+                      local_nonlinear_kernel4<DIM, N><<<gb, nw * 32, smem, C->stream>>>(op, T3, wJ, rqg, C->loc.as<double>(), C->bloc.as<double>(), cpw); break;
+                EXTFEM_NL4(1) EXTFEM_NL4(2) EXTFEM_NL4(3) EXTFEM_NL4(4)
+#undef EXTFEM_NL4
+                }
+                return;
+            }
+        }
+        if (v3 && !(C->nl_version >= 4 && T3.dense_ok && nl4_points_ok)) {   // (with the dense tables the sparse ones of v3 were not built)
             const size_t wd = nl3_warp_doubles(op.nq, op.nin, op.nout, op.NC, op.NR, T3.EC, T3.ER, T3.same, T3.phi_off[T3.nspaces]);
             int nw = 8;
             while (nw > 1 && (size_t)nw * wd * 8 + T3.tab_bytes > 100 * 1024) nw >>= 1;

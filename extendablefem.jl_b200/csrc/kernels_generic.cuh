@@ -148,6 +148,7 @@ __device__ __forceinline__ void lin_apply(int id, const double *x, const double 
 __device__ __forceinline__ void nl_apply(int id, int dim, const double *in, const double *p, double *val, double *J,
                                          int nin, int nout, int region = 1)
 {
+#pragma unroll
     for (int i = 0; i < nin * nout; ++i) J[i] = 0.0;
     switch (id) {
     case EXTFEM_NL_NSE2D: {
@@ -191,6 +192,7 @@ __device__ __forceinline__ void nl_apply(int id, int dim, const double *in, cons
         // D2W = mu I + c * d(dd)/dF + dd (x) dd * (lambda + mu - lambda log(det)) / det^2
         double mu = p[0], la = p[1];
         double F[9];
+#pragma unroll
         for (int i = 0; i < 9; ++i) F[i] = in[i];
         F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
         double dd[9];
@@ -207,8 +209,11 @@ __device__ __forceinline__ void nl_apply(int id, int dim, const double *in, cons
         double ld = log(det);
         double c = (la * ld - mu) / det;
         double e = (la + mu - la * ld) / (det * det);
+#pragma unroll
         for (int i = 0; i < 9; ++i) val[i] = mu * F[i] + c * dd[i];
+#pragma unroll
         for (int i = 0; i < 9; ++i) {
+#pragma unroll
             for (int j = 0; j < 9; ++j) J[i * 9 + j] = e * dd[i] * dd[j];
             J[i * 9 + i] += mu;
         }
@@ -229,12 +234,14 @@ __device__ __forceinline__ void nl_apply(int id, int dim, const double *in, cons
         val[0] = in[0] * in[1] + in[0];
         J[0 * nin + 0] = in[1] + 1.0;
         J[0 * nin + 1] = in[0];
+#pragma unroll
         for (int d = 0; d < dim; ++d) { val[1 + d] = in[1 + d]; J[(1 + d) * nin + 1 + d] = 1.0; }
     } break;
     case EXTFEM_NL_NLPOISSON105: {
         const double ep = exp(in[0]), em = exp(-in[0]);
         val[0] = ep - em;
         J[0] = ep + em;
+#pragma unroll
         for (int d = 0; d < dim; ++d) { val[1 + d] = p[0] * in[1 + d]; J[(1 + d) * nin + 1 + d] = p[0]; }
     } break;
     case EXTFEM_NL_STVENANT230: {
@@ -247,6 +254,7 @@ __device__ __forceinline__ void nl_apply(int id, int dim, const double *in, cons
         const double a = la * (e1 + e2) + 2.0 * mu * e1, b = la * (e1 + e2) + 2.0 * mu * e2, c = 2.0 * mu * e3;
         val[0] = a; val[1] = c; val[2] = c; val[3] = b;
         const double d1[4] = {1.0 + g1, 0.0, g3, 0.0}, d2[4] = {0.0, g2, 0.0, 1.0 + g4}, d3[4] = {g2, 1.0 + g1, 1.0 + g4, g3};
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
             J[0 * 4 + j] = (la + 2.0 * mu) * d1[j] + la * d2[j];
             J[3 * 4 + j] = la * d1[j] + (la + 2.0 * mu) * d2[j];
@@ -730,6 +738,11 @@ struct NL3Tables {
     int o_enb, o_eng;                          // u16 [NR*NC][ER]: offsets of BT[0][x][k] and of GJ[0][j][out_x(k)]
     int o_uptr, o_ulist;                       // input_args: per result index o the (j | x << 8) pairs with out == o
     int o_ucol;                                // i32 [NC]: offset of the column dof in the cell's solution gather (block, dof)
+    // dense form of the operator matrix for the tensor-core kernel (local_nonlinear_kernel4): B[(q, component)][dof], row
+    // stride Np4 (== 4 mod 16: conflict-free fragment loads), Kp4 = nq * nin rounded up to a multiple of 4
+    int dense_ok, NT4, Np4;                    // tensor-core path: number of 8-wide dof tiles and the row stride of B_q
+    int o_ddst;                                // u16 [EC][NC]: offset of the sparse entry inside the dense B_q
+    int o_pt;                                  // u8x4 [EC][NC]: (space, scalar basis function, source 0 value | 1+d gradient, -) of a B entry
     int nspaces, ns[NL2_MAXSP_];
     const double *refvals[NL2_MAXSP_], *refgrads[NL2_MAXSP_];
     int phi_off[NL2_MAXSP_ + 1];
@@ -869,6 +882,242 @@ local_nonlinear_kernel3(const __grid_constant__ OpDev op, const __grid_constant_
             bout[k] = G.visited ? acc : 0.0;
         }
         __syncwarp();
+    }
+}
+
+// ---- NonlinearOperator on FP64 tensor cores (v4) -------------------------------------------------------------------------
+// Two kernels.
+//  (1) nl_point_kernel<DIM, NIO>: one THREAD per (cell, quadrature point): input_args from the solution, kernel value and analytic
+//      Jacobian in registers (nonlinear_operator.jl:343-369), stores w_q J_q and (J u - F) factor w_q |T| as structure-of-arrays
+//      [entry][cell * nq + q] (coalesced writes; the reader below fetches the nq values of one cell as whole sectors).  Every lane
+//      works -- in the warp-per-cell kernels this phase ran on nq of 32 lanes through shared-memory read-modify-write chains and
+//      cost more than all contractions together.
+//  (2) local_nonlinear_kernel4<DIM>: one warp per cell, the two contractions of nonlinear_operator.jl:372-401 as dense GEMMs on
+//      mma.sync.m8n8k4.f64 (DMMA):
+//          GJ_q = (w_q J_q) B_q          [nout x nin] x [nin x NC]   per quadrature point
+//          A    = sum_q B_q^T GJ_q       [NR x (nq nout)] x [(nq nout) x NC]
+//      where B[(q, component)][dof] is the operator matrix of the cell (values / physical gradients of the basis functions routed to
+//      the components of the kernel's input vector): the sparse B tables written into a zero-initialised dense array whose zero
+//      pattern is cell-independent.  Used when test and args describe the same operators (T.same: the usual Newton setting).
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// nl_apply with compile-time vector lengths and the kernel id folded per case: after inlining every index is static, the value and
+// Jacobian arrays live in registers
+template <int DIM, int NIO>
+__device__ __forceinline__ void nl_apply_fixed(int id, const double (&u)[NIO], const double *p, double (&val)[NIO], double (&J)[NIO * NIO], int region)
+{
+    switch (id) {
+    case EXTFEM_NL_NSE2D: if constexpr (NIO == 7) nl_apply(EXTFEM_NL_NSE2D, DIM, u, p, val, J, NIO, NIO, region); break;
+    case EXTFEM_NL_LINNSE7: if constexpr (NIO == 7) nl_apply(EXTFEM_NL_LINNSE7, DIM, u, p, val, J, NIO, NIO, region); break;
+    case EXTFEM_NL_NEOHOOKE3D: if constexpr (NIO == 9) nl_apply(EXTFEM_NL_NEOHOOKE3D, DIM, u, p, val, J, NIO, NIO, region); break;
+    case EXTFEM_NL_RCD: if constexpr (NIO == 1 + DIM) nl_apply(EXTFEM_NL_RCD, DIM, u, p, val, J, NIO, NIO, region); break;
+    case EXTFEM_NL_NLPOISSON105: if constexpr (NIO == 1 + DIM) nl_apply(EXTFEM_NL_NLPOISSON105, DIM, u, p, val, J, NIO, NIO, region); break;
+    case EXTFEM_NL_STVENANT230: if constexpr (NIO == 4) nl_apply(EXTFEM_NL_STVENANT230, DIM, u, p, val, J, NIO, NIO, region); break;
+    }
+}
+
+template <int DIM, int NIO>
+__global__ void __launch_bounds__(128)
+nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tables T, double *__restrict__ wJ, double *__restrict__ rqg)
+{
+    extern __shared__ __align__(16) unsigned char tb[];
+    for (int i = threadIdx.x; i < T.tab_bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(tb)[i] = __ldg(reinterpret_cast<const uint4 *>(T.tab) + i);
+    const unsigned short *uptr = reinterpret_cast<const unsigned short *>(tb + T.o_uptr), *ulist = reinterpret_cast<const unsigned short *>(tb + T.o_ulist);
+    const uchar4 *pt = reinterpret_cast<const uchar4 *>(tb + T.o_pt);
+    const double *bgsc = reinterpret_cast<const double *>(tb + T.o_bgsc);
+    double *solc = reinterpret_cast<double *>(tb + T.tab_bytes);      // [cells of the block][NC] solution coefficients
+    const int nq = op.nq, NC = T.NC;
+    const long long ntot = op.ncells * nq;
+    const long long t0 = (long long)blockIdx.x * blockDim.x, t = t0 + threadIdx.x;
+    const long long c0 = t0 / nq, c1 = min((t0 + blockDim.x - 1) / nq, op.ncells - 1);
+    // the coefficients of the block's cells, one independent load per (cell, dof)
+    for (int i = threadIdx.x; i < (int)(c1 - c0 + 1) * NC; i += blockDim.x) {
+        const int c = i / NC, j = i - c * NC;
+        int b = 0;
+        while (b + 1 < T.ncolblocks && j >= T.blk_locoff[b] + T.blk_nd[b]) ++b;
+        solc[i] = op.sol[T.blk_soloff[b] + T.blk_celldofs[b][(c0 + c) * T.blk_nd[b] + (j - T.blk_locoff[b])]];
+    }
+    __syncthreads();
+    if (t >= ntot) return;
+    const long long cell = t / nq;
+    const int q = (int)(t - cell * nq);
+    const double *sc_ = solc + (size_t)(cell - c0) * NC;
+    CellGeo<DIM> G;
+    load_geo<DIM>(op, cell, G);
+    // input_args: for every component o the (dof, entry) pairs that feed it (static register index)
+    double u[NIO];
+#pragma unroll
+    for (int o = 0; o < NIO; ++o) {
+        double a = 0.0;
+        for (int p = uptr[o]; p < uptr[o + 1]; ++p) {
+            const int j = ulist[p] & 0xff, x = ulist[p] >> 8;
+            const uchar4 e = pt[x * NC + j];
+            double v;
+            if (e.z == 0) v = __ldg(T.refvals[e.x] + q * T.ns[e.x] + e.y);
+            else {
+                const double *rg = T.refgrads[e.x] + ((size_t)q * T.ns[e.x] + e.y) * DIM;
+                double r_[DIM];
+#pragma unroll
+                for (int r = 0; r < DIM; ++r) r_[r] = __ldg(rg + r);
+                v = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)          // select the column of A^-1 without a dynamic register index
+                    if (e.z - 1 == d) {
+#pragma unroll
+                        for (int r = 0; r < DIM; ++r) v = fma(G.Ainv[r * DIM + d], r_[r], v);
+                    }
+            }
+            a = fma(sc_[j] * bgsc[x * NC + j], v, a);
+        }
+        u[o] = a;
+    }
+    double val[NIO], J[NIO * NIO];
+    nl_apply_fixed<DIM, NIO>(op.kernel_id, u, op.params, val, J, op.cellregions[cell]);
+    const double w = op.qw[q], sc = op.factor * w * G.vol;
+#pragma unroll
+    for (int k = 0; k < NIO; ++k) {
+        double sum = 0.0;
+#pragma unroll
+        for (int d = 0; d < NIO; ++d) {
+            sum = fma(J[k * NIO + d], u[d], sum);
+            wJ[(size_t)(k * NIO + d) * ntot + t] = J[k * NIO + d] * w;
+        }
+        rqg[(size_t)k * ntot + t] = (sum - val[k]) * sc;
+    }
+}
+
+// doubles of shared memory per warp: PHI | B_q [rows][Np] | GJ_q [rows][Np] | w J [nq][nout][nin] | residual terms [nq][nout]
+__host__ __device__ inline size_t nl4_warp_doubles(int nq, int nin, int nout, int Np, int phid)
+{
+    const int rows = (nin + 3) / 4 * 4;
+    size_t d = (size_t)(phid + (phid & 1)) + 2 * (size_t)rows * Np + (size_t)nq * nin * nout + (size_t)nq * nout;
+    return (d + 1) & ~(size_t)1;
+}
+
+// NT = number of 8-wide dof tiles (NR = NC <= 8 NT); the NT x NT accumulator tiles of the cell matrix stay in registers over the
+// quadrature loop, B_q and GJ_q exist for one point at a time (rows = nin rounded up to the k-step of 4).
+template <int DIM, int NT>
+__global__ void __launch_bounds__(128, 4)
+local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tables T, const double *__restrict__ wJ,
+                        const double *__restrict__ rqg, double *__restrict__ loc, double *__restrict__ bloc, int cells_per_warp)
+{
+    constexpr int Np = NT <= 2 ? 20 : 36;      // row stride = 4 mod 16 doubles: the fragment loads below are bank-conflict free
+    extern __shared__ __align__(16) double smem_d[];
+    const int nin = op.nin, nout = op.nout, JS = nin * nout, nq = op.nq, NR = T.NR, NC = T.NC, NRC = NR * NC, ECNC = T.EC * NC;
+    const int KS = (nin + 3) / 4, rows = KS * 4, MT = (nout + 7) / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int phid = T.phi_off[T.nspaces];
+    const size_t wd = nl4_warp_doubles(nq, nin, nout, Np, phid);
+    unsigned char *tb = reinterpret_cast<unsigned char *>(smem_d + (size_t)nwarp * wd);
+    for (int i = threadIdx.x; i < T.tab_bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(tb)[i] = __ldg(reinterpret_cast<const uint4 *>(T.tab) + i);
+    const int *bgidx = reinterpret_cast<const int *>(tb + T.o_bgidx);
+    const double *bgsc = reinterpret_cast<const double *>(tb + T.o_bgsc);
+    const unsigned short *ddst = reinterpret_cast<const unsigned short *>(tb + T.o_ddst);
+    double *PHI = smem_d + (size_t)warp * wd;
+    double *Bq = PHI + phid + (phid & 1);      // [rows][Np] operator matrix of one quadrature point (16-byte aligned)
+    double *Gq = Bq + rows * Np;               // [rows][Np] (w J_q) B_q
+    double *Jq = Gq + rows * Np;               // [nq][nout][nin]
+    double *rq = Jq + (size_t)nq * JS;         // [nq][nout] (J u - F) factor w |T|
+    for (int i = lane; i < 2 * rows * Np; i += 32) Bq[i] = 0.0;   // structural zeros and padding stay zero for every cell and point
+    __syncthreads();
+    const int gid = lane >> 2, tig = lane & 3;
+    const long long ntot = op.ncells * nq;
+    const long long cbase = ((long long)blockIdx.x * nwarp + warp) * cells_per_warp;
+    for (int ci = 0; ci < cells_per_warp; ++ci) {
+        const long long cell = cbase + ci;
+        if (cell >= op.ncells) break;
+        CellGeo<DIM> G;
+        load_geo<DIM>(op, cell, G);
+        __syncwarp();
+        // w J and the residual terms of the cell's points (written by nl_point_kernel)
+        for (int i = lane; i < JS * nq; i += 32) {
+            const int e = i / nq, q = i - e * nq;
+            Jq[q * JS + e] = __ldg(wJ + (size_t)e * ntot + cell * nq + q);
+        }
+        for (int i = lane; i < nout * nq; i += 32) {
+            const int k = i / nq, q = i - k * nq;
+            rq[q * nout + k] = __ldg(rqg + (size_t)k * ntot + cell * nq + q);
+        }
+        for (int sp = 0; sp < T.nspaces; ++sp) {
+            double *ph = PHI + T.phi_off[sp];
+            for (int e = lane; e < nq * T.ns[sp]; e += 32) {
+                double *o = ph + (size_t)e * (1 + DIM);
+                o[0] = __ldg(T.refvals[sp] + e);
+                const double *rg = T.refgrads[sp] + (size_t)e * DIM;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    double g = 0.0;
+#pragma unroll
+                    for (int r = 0; r < DIM; ++r) g += G.Ainv[r * DIM + d] * __ldg(rg + r);
+                    o[1 + d] = g;
+                }
+            }
+        }
+        double acc[NT][NT][2];
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+            for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        double racc = 0.0;
+        __syncwarp();
+        for (int q = 0; q < nq; ++q) {
+            // operator matrix of the point: the sparse entries of the B tables into their dense places
+            for (int i = lane; i < ECNC; i += 32) { const int p = bgidx[q * ECNC + i]; if (p >= 0) Bq[ddst[i]] = bgsc[i] * PHI[p]; }
+            __syncwarp();
+            // GJ_q = (w J_q) B_q: tiles of 8 components x 8 dofs, k-steps of 4 input components
+            const double *J = Jq + (size_t)q * JS;
+            for (int mt = 0; mt < MT; ++mt) {
+                const int o = mt * 8 + gid;
+                double g[NT][2];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) g[t][0] = g[t][1] = 0.0;
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int i = ks * 4 + tig;
+                    const double a = (o < nout && i < nin) ? J[o * nin + i] : 0.0;
+                    const double *pb = Bq + i * Np + gid;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) dmma_m8n8k4(g[t][0], g[t][1], a, pb[t * 8]);
+                }
+                if (o < rows) {
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) *reinterpret_cast<double2 *>(Gq + o * Np + t * 8 + 2 * tig) = make_double2(g[t][0], g[t][1]);
+                }
+            }
+            __syncwarp();
+            // A += B_q^T GJ_q: every 8 x 8 tile of the cell matrix, k-steps of 4 components
+            for (int ks = 0; ks < KS; ++ks) {
+                const double *pa = Bq + (ks * 4 + tig) * Np + gid, *pg = Gq + (ks * 4 + tig) * Np + gid;
+                double av[NT], bv[NT];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) { av[t] = pa[t * 8]; bv[t] = pg[t * 8]; }
+#pragma unroll
+                for (int a = 0; a < NT; ++a)
+#pragma unroll
+                    for (int b = 0; b < NT; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], av[a], bv[b]);
+            }
+            // rhs_k += sum_component (J u - F) B
+            if (lane < NR) {
+                const double *r = rq + q * nout;
+                for (int o = 0; o < nout; ++o) racc = fma(r[o], Bq[o * Np + lane], racc);
+            }
+            __syncwarp();
+        }
+        const double fv = G.visited ? op.factor * G.vol : 0.0;
+        double *out = loc + (size_t)cell * NRC;
+#pragma unroll
+        for (int a = 0; a < NT; ++a) {
+            const int k = a * 8 + gid;
+#pragma unroll
+            for (int b = 0; b < NT; ++b) {
+                const int j = b * 8 + 2 * tig;
+                if (k < NR && j < NC) out[(size_t)j * NR + k] = acc[a][b][0] * fv;
+                if (k < NR && j + 1 < NC) out[(size_t)(j + 1) * NR + k] = acc[a][b][1] * fv;
+            }
+        }
+        if (lane < NR) bloc[(size_t)cell * NR + lane] = G.visited ? racc : 0.0;
     }
 }
 

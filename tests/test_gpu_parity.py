@@ -326,15 +326,15 @@ def test_nonlinear_local_kernel_versions_agree(pkg, ora, engine, case):
         desc = engine.make_opdesc(args, args=args, kernel_id=pkg.lib.kernel_id("neohooke3d"), params=[3.8, 5.7], regions=(1,))
     res = {}
     try:
-        for ver in (1, 2, 3):     # entry-wise | staged per block | warp per cell (default)
+        for ver in (1, 2, 3, 4):     # entry-wise | staged per block | warp per cell | warp per cell on FP64 tensor cores (default)
             engine.set_option("nonlinear_kernel", ver)
             a = np.empty(S.rowval.size); b = np.empty(S.N)
             engine.assemble_nonlinear(S.pat, desc, sol, nzval_out=a, b_out=b)
             res[ver] = (a, b)
     finally:
-        engine.set_option("nonlinear_kernel", 3)
+        engine.set_option("nonlinear_kernel", 4)
     a1, b1 = res[1]
-    for ver in (2, 3):
+    for ver in (2, 3, 4):
         check_values(res[ver][0], a1, rtol=1e-13, what=f"jacobian v{ver} vs v1")
         check_values(res[ver][1], b1, rtol=1e-13, scale=max(np.abs(b1).max(), np.abs(a1).max() * np.abs(sol).max()), what=f"rhs v{ver} vs v1")
 

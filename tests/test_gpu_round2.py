@@ -101,14 +101,14 @@ def test_stvenant230_kernel(pkg, ora, engine):
                                          csc=(S.colptr, S.rowval))
     check_values(nz, nzref, what="stvenant230 jacobian")
     check_values(b, bref, what="stvenant230 rhs")
-    for ver in (1, 2):
+    for ver in (1, 2, 3):
         engine.set_option("nonlinear_kernel", ver)
         try:
             a2 = np.empty(S.rowval.size)
             engine.assemble_nonlinear(S.pat, engine.make_opdesc(args, args=args, kernel_id=pkg.lib.kernel_id("stvenant230"), params=params),
                                       sol, nzval_out=a2)
         finally:
-            engine.set_option("nonlinear_kernel", 3)
+            engine.set_option("nonlinear_kernel", 4)
         check_values(a2, nzref, what=f"stvenant230 jacobian, local kernel v{ver}")
 
 
