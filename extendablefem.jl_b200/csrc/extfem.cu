@@ -1421,7 +1421,7 @@ static int build_nl3_tables(Ctx *ctx, const OpDev &op, NL3Tables &T, bool *ok, b
     {   // dense operator matrix of the tensor-core kernel (kernels_generic.cuh: local_nonlinear_kernel4)
         T.NT4 = (std::max(op.NC, op.NR) + 7) / 8;
         T.Np4 = T.NT4 <= 2 ? 20 : 36;
-        T.dense_ok = same && op.nin == op.nout && op.nin <= 16 && T.NT4 <= 4 && nl4_warp_doubles(op.nq, op.nin, op.nout, T.Np4, off) * 8 * 4 <= 120 * 1024;
+        T.dense_ok = same && op.nin == op.nout && op.nin <= 9 && T.NT4 <= 4 && nl4_warp_doubles(op.nq, op.nin, T.Np4, off) * 8 * 4 <= 120 * 1024;
         T.o_pt = reserve((size_t)T.EC * op.NC * 4);
         for (int x = 0; x < T.EC; ++x)
             for (int j = 0; j < op.NC; ++j) {
@@ -2280,7 +2280,7 @@ int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc 
     int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
         constexpr int DIM = decltype(dimc)::value;
         if (v3 && C->nl_version >= 4 && T3.dense_ok && nl4_points_ok) {
-            const size_t wd = nl4_warp_doubles(op.nq, op.nin, op.nout, T3.Np4, T3.phi_off[T3.nspaces]);
+            const size_t wd = nl4_warp_doubles(op.nq, op.nin, T3.Np4, T3.phi_off[T3.nspaces]);
             const int nw = 4, cpw = 8;
             const size_t smem = (size_t)nw * wd * 8 + T3.tab_bytes;
             if (smem <= 220 * 1024) {
@@ -2295,14 +2295,15 @@ int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc 
 #undef EXTFEM_NLPT
                 }
                 ++C->launches;
-                // (2) contractions on the FP64 tensor cores, one warp per cell
+                // (2) contractions on the FP64 tensor cores, one warp per cell: k-steps / rank-1 remainder by the kernel's vector length
                 const unsigned gb = nblocks(op.ncells, nw * cpw);
-                switch (T3.NT4) {
-#define EXTFEM_NL4(N) case N: smem_attr(C, (const void *)local_nonlinear_kernel4<DIM, N>, 227 * 1024); \
-                      local_nonlinear_kernel4<DIM, N><<<gb, nw * 32, smem, C->stream>>>(op, T3, wJ, rqg, C->loc.as<double>(), C->bloc.as<double>(), cpw); break;
-                EXTFEM_NL4(1) EXTFEM_NL4(2) EXTFEM_NL4(3) EXTFEM_NL4(4)
+                const int shape = op.nin <= 4 ? 0 : (op.nin <= 8 ? 1 : 2);
+#define EXTFEM_NL4(N, KS, R1) smem_attr(C, (const void *)local_nonlinear_kernel4<DIM, N, KS, R1>, 227 * 1024); \
+                      local_nonlinear_kernel4<DIM, N, KS, R1><<<gb, nw * 32, smem, C->stream>>>(op, T3, wJ, rqg, C->loc.as<double>(), C->bloc.as<double>(), cpw);
+#define EXTFEM_NL4S(N) case N: if (shape == 0) { EXTFEM_NL4(N, 1, false) } else if (shape == 1) { EXTFEM_NL4(N, 2, false) } else { EXTFEM_NL4(N, 2, true) } break;
+                switch (T3.NT4) { EXTFEM_NL4S(1) EXTFEM_NL4S(2) EXTFEM_NL4S(3) EXTFEM_NL4S(4) }
+#undef EXTFEM_NL4S
 #undef EXTFEM_NL4
-                }
                 return;
             }
         }

@@ -989,28 +989,34 @@ nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tab
     }
 }
 
-// doubles of shared memory per warp: PHI | B_q [rows][Np] | GJ_q [rows][Np] | w J [nq][nout][nin] | residual terms [nq][nout]
-__host__ __device__ inline size_t nl4_warp_doubles(int nq, int nin, int nout, int Np, int phid)
+// doubles of shared memory per warp: PHI | B_q [rows][Np] | GJ_q [rows][Np] | w J [nq][nin][nin] | residual terms [nq][nin]
+__host__ __device__ inline size_t nl4_warp_doubles(int nq, int nin, int Np, int phid)
 {
     const int rows = (nin + 3) / 4 * 4;
-    size_t d = (size_t)(phid + (phid & 1)) + 2 * (size_t)rows * Np + (size_t)nq * nin * nout + (size_t)nq * nout;
+    size_t d = (size_t)(phid + (phid & 1)) + 2 * (size_t)rows * Np + (size_t)nq * nin * nin + (size_t)nq * nin;
     return (d + 1) & ~(size_t)1;
 }
 
 // NT = number of 8-wide dof tiles (NR = NC <= 8 NT); the NT x NT accumulator tiles of the cell matrix stay in registers over the
-// quadrature loop, B_q and GJ_q exist for one point at a time (rows = nin rounded up to the k-step of 4).
-template <int DIM, int NT>
+// quadrature loop, B_q and GJ_q exist for one point at a time.  KS = k-steps of 4 kernel components done on the tensor cores;
+// R1: one more component (nin = 4 KS + 1, e.g. the 9 gradient components of a 3D displacement) handled as a rank-1 update on
+// the FP64 FMA pipe instead of a padded k-step (B200: DMMA and DFMA share one peak, padding is paid in full).
+// The right-hand side rides along as column NC of GJ_q when the last dof tile has a free column.
+template <int DIM, int NT, int KS, bool R1>
 __global__ void __launch_bounds__(128, 4)
 local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tables T, const double *__restrict__ wJ,
                         const double *__restrict__ rqg, double *__restrict__ loc, double *__restrict__ bloc, int cells_per_warp)
 {
     constexpr int Np = NT <= 2 ? 20 : 36;      // row stride = 4 mod 16 doubles: the fragment loads below are bank-conflict free
+    constexpr int KD = KS * 4;                 // components on the tensor cores
+    constexpr int MT = (KD + 7) / 8;           // 8-row tiles of GJ_q
+    constexpr int rows = (KD + (R1 ? 1 : 0) + 3) / 4 * 4;
     extern __shared__ __align__(16) double smem_d[];
-    const int nin = op.nin, nout = op.nout, JS = nin * nout, nq = op.nq, NR = T.NR, NC = T.NC, NRC = NR * NC, ECNC = T.EC * NC;
-    const int KS = (nin + 3) / 4, rows = KS * 4, MT = (nout + 7) / 8;
+    const int nin = op.nin, nq = op.nq, NR = T.NR, NC = T.NC, NRC = NR * NC, ECNC = T.EC * NC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int phid = T.phi_off[T.nspaces];
-    const size_t wd = nl4_warp_doubles(nq, nin, nout, Np, phid);
+    const size_t wd = nl4_warp_doubles(nq, nin, Np, phid);
+    const int JS = nin * nin;
     unsigned char *tb = reinterpret_cast<unsigned char *>(smem_d + (size_t)nwarp * wd);
     for (int i = threadIdx.x; i < T.tab_bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(tb)[i] = __ldg(reinterpret_cast<const uint4 *>(T.tab) + i);
     const int *bgidx = reinterpret_cast<const int *>(tb + T.o_bgidx);
@@ -1019,11 +1025,15 @@ local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant_
     double *PHI = smem_d + (size_t)warp * wd;
     double *Bq = PHI + phid + (phid & 1);      // [rows][Np] operator matrix of one quadrature point (16-byte aligned)
     double *Gq = Bq + rows * Np;               // [rows][Np] (w J_q) B_q
-    double *Jq = Gq + rows * Np;               // [nq][nout][nin]
-    double *rq = Jq + (size_t)nq * JS;         // [nq][nout] (J u - F) factor w |T|
+    double *Jq = Gq + rows * Np;               // [nq][nin][nin] w J of the cell's points
+    double *rq = Jq + (size_t)nq * JS;         // [nq][nin] (J u - F) factor w |T|
     for (int i = lane; i < 2 * rows * Np; i += 32) Bq[i] = 0.0;   // structural zeros and padding stay zero for every cell and point
     __syncthreads();
     const int gid = lane >> 2, tig = lane & 3;
+    // the lane whose accumulator fragment holds column NC carries the right-hand side
+    const bool rhs_in_gemm = (NC & 7) != 0;
+    const int rt = NC >> 3, rslot = NC & 1;
+    const bool rmine = rhs_in_gemm && ((NC & 7) >> 1) == tig;
     const long long ntot = op.ncells * nq;
     const long long cbase = ((long long)blockIdx.x * nwarp + warp) * cells_per_warp;
     for (int ci = 0; ci < cells_per_warp; ++ci) {
@@ -1032,14 +1042,22 @@ local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant_
         CellGeo<DIM> G;
         load_geo<DIM>(op, cell, G);
         __syncwarp();
-        // w J and the residual terms of the cell's points (written by nl_point_kernel)
-        for (int i = lane; i < JS * nq; i += 32) {
-            const int e = i / nq, q = i - e * nq;
-            Jq[q * JS + e] = __ldg(wJ + (size_t)e * ntot + cell * nq + q);
-        }
-        for (int i = lane; i < nout * nq; i += 32) {
-            const int k = i / nq, q = i - k * nq;
-            rq[q * nout + k] = __ldg(rqg + (size_t)k * ntot + cell * nq + q);
+        {   // w J and the residual terms of the cell's points (nl_point_kernel wrote [entry][cell nq + q]); (entry, q) advance
+            // with the lane stride without a division
+            const double *wJc = wJ + cell * nq, *rqc = rqg + cell * nq;
+            const int de = 32 / nq, dq = 32 - de * nq;
+            int e = lane / nq, q = lane - e * nq;
+            for (int i = lane; i < JS * nq; i += 32) {
+                Jq[q * JS + e] = __ldg(wJc + (size_t)e * ntot + q);
+                e += de; q += dq;
+                if (q >= nq) { q -= nq; ++e; }
+            }
+            e = lane / nq; q = lane - e * nq;
+            for (int i = lane; i < nin * nq; i += 32) {
+                rq[q * nin + e] = __ldg(rqc + (size_t)e * ntot + q);
+                e += de; q += dq;
+                if (q >= nq) { q -= nq; ++e; }
+            }
         }
         for (int sp = 0; sp < T.nspaces; ++sp) {
             double *ph = PHI + T.phi_off[sp];
@@ -1064,30 +1082,58 @@ local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant_
         double racc = 0.0;
         __syncwarp();
         for (int q = 0; q < nq; ++q) {
+            // this lane's fragment of w J_q (component rows gid [+8], input columns 4 ks + tig) and its residual terms
+            const double *J = Jq + q * JS, *j8 = J + KD * nin, *r = rq + q * nin;
+            double ja[MT][KS], jr[MT], rr[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int o = mt * 8 + gid;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int i = ks * 4 + tig;
+                    ja[mt][ks] = (o < nin && i < nin) ? J[o * nin + i] : 0.0;
+                }
+                jr[mt] = (R1 && o < nin) ? J[o * nin + KD] : 0.0;
+                rr[mt] = (rmine && o < nin) ? r[o] : 0.0;
+            }
             // operator matrix of the point: the sparse entries of the B tables into their dense places
             for (int i = lane; i < ECNC; i += 32) { const int p = bgidx[q * ECNC + i]; if (p >= 0) Bq[ddst[i]] = bgsc[i] * PHI[p]; }
             __syncwarp();
             // GJ_q = (w J_q) B_q: tiles of 8 components x 8 dofs, k-steps of 4 input components
-            const double *J = Jq + (size_t)q * JS;
+#pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                const int o = mt * 8 + gid;
                 double g[NT][2];
 #pragma unroll
                 for (int t = 0; t < NT; ++t) g[t][0] = g[t][1] = 0.0;
+#pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                    const int i = ks * 4 + tig;
-                    const double a = (o < nout && i < nin) ? J[o * nin + i] : 0.0;
-                    const double *pb = Bq + i * Np + gid;
+                    const double *pb = Bq + (ks * 4 + tig) * Np + gid;
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) dmma_m8n8k4(g[t][0], g[t][1], a, pb[t * 8]);
+                    for (int t = 0; t < NT; ++t) dmma_m8n8k4(g[t][0], g[t][1], ja[mt][ks], pb[t * 8]);
                 }
-                if (o < rows) {
+                if (R1) {
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) *reinterpret_cast<double2 *>(Gq + o * Np + t * 8 + 2 * tig) = make_double2(g[t][0], g[t][1]);
+                    for (int t = 0; t < NT; ++t) {
+                        const double2 b8 = *reinterpret_cast<const double2 *>(Bq + KD * Np + t * 8 + 2 * tig);
+                        g[t][0] = fma(jr[mt], b8.x, g[t][0]);
+                        g[t][1] = fma(jr[mt], b8.y, g[t][1]);
+                    }
                 }
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    if (t == rt && rmine) { if (rslot) g[t][1] = rr[mt]; else g[t][0] = rr[mt]; }
+                    if (mt * 8 + gid < rows) *reinterpret_cast<double2 *>(Gq + (mt * 8 + gid) * Np + t * 8 + 2 * tig) = make_double2(g[t][0], g[t][1]);
+                }
+            }
+            if (R1 && lane < NT * 8) {          // last component row on the FMA pipe
+                double g = 0.0;
+                for (int i = 0; i < nin; ++i) g = fma(j8[i], Bq[i * Np + lane], g);
+                if (rhs_in_gemm && lane == NC) g = r[KD];
+                Gq[KD * Np + lane] = g;
             }
             __syncwarp();
             // A += B_q^T GJ_q: every 8 x 8 tile of the cell matrix, k-steps of 4 components
+#pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 const double *pa = Bq + (ks * 4 + tig) * Np + gid, *pg = Gq + (ks * 4 + tig) * Np + gid;
                 double av[NT], bv[NT];
@@ -1098,15 +1144,29 @@ local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant_
 #pragma unroll
                     for (int b = 0; b < NT; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], av[a], bv[b]);
             }
-            // rhs_k += sum_component (J u - F) B
-            if (lane < NR) {
-                const double *r = rq + q * nout;
-                for (int o = 0; o < nout; ++o) racc = fma(r[o], Bq[o * Np + lane], racc);
+            if (R1) {
+                double av[NT];
+                double2 bv[NT];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    av[t] = Bq[KD * Np + t * 8 + gid];
+                    bv[t] = *reinterpret_cast<const double2 *>(Gq + KD * Np + t * 8 + 2 * tig);
+                }
+#pragma unroll
+                for (int a = 0; a < NT; ++a)
+#pragma unroll
+                    for (int b = 0; b < NT; ++b) {
+                        acc[a][b][0] = fma(av[a], bv[b].x, acc[a][b][0]);
+                        acc[a][b][1] = fma(av[a], bv[b].y, acc[a][b][1]);
+                    }
             }
+            if (!rhs_in_gemm && lane < NR)     // no free column: rhs_k += sum_component (J u - F) B
+                for (int o = 0; o < nin; ++o) racc = fma(r[o], Bq[o * Np + lane], racc);
             __syncwarp();
         }
         const double fv = G.visited ? op.factor * G.vol : 0.0;
         double *out = loc + (size_t)cell * NRC;
+        double *bout = bloc + (size_t)cell * NR;
 #pragma unroll
         for (int a = 0; a < NT; ++a) {
             const int k = a * 8 + gid;
@@ -1115,9 +1175,10 @@ local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant_
                 const int j = b * 8 + 2 * tig;
                 if (k < NR && j < NC) out[(size_t)j * NR + k] = acc[a][b][0] * fv;
                 if (k < NR && j + 1 < NC) out[(size_t)(j + 1) * NR + k] = acc[a][b][1] * fv;
+                if (b == rt && rmine && k < NR) bout[k] = G.visited ? (rslot ? acc[a][b][1] : acc[a][b][0]) : 0.0;
             }
         }
-        if (lane < NR) bloc[(size_t)cell * NR + lane] = G.visited ? racc : 0.0;
+        if (!rhs_in_gemm && lane < NR) bout[lane] = G.visited ? racc : 0.0;
     }
 }
 
