@@ -128,6 +128,7 @@ struct Ctx {
     DevBuf custom_qw, custom_qx;
     DevBuf loc, bloc, sol, params_scratch, tab, geo, visit, fq;
     bool fast_enabled = true;   // option "fastpath"
+    bool gather_warp = true;    // option "gather_warp": generic matrix reduction with one warp (1) / one thread (0) per column
     int nl_version = 4;         // option "nonlinear_kernel": 1 entry-wise local kernel, 2 staged per block, 3 warp per cell,
                                 // 4 warp per cell with the contractions on FP64 tensor cores (falls back to 3 when not applicable)
     DevBuf nl2buf;
@@ -592,7 +593,14 @@ static int launch_gather_cols(Ctx *ctx, Pattern &P, const Prepared &R, int overw
         for (int j = 0; j < nd; ++j, ++t) { g.rowmap[t] = P.rowlocoff[b] + j; g.rowsrc[t] = rowsideoff[i] + j; }
     }
     g.nrows_g = t;
-    gather_columns_kernel<PosT><<<P.nchunks, GATHER_THREADS, 0, ctx->stream>>>(g);
+    if (g.nrows_g >= 8 && ctx->gather_warp) {
+        const bool two = g.nrows_g <= 16;
+        if (transposed) { if (two) gather_columns_warp_kernel<PosT, true, 2><<<P.nchunks, GATHER_WARP_THREADS, 0, ctx->stream>>>(g);
+                          else gather_columns_warp_kernel<PosT, true, 1><<<P.nchunks, GATHER_WARP_THREADS, 0, ctx->stream>>>(g); }
+        else { if (two) gather_columns_warp_kernel<PosT, false, 2><<<P.nchunks, GATHER_WARP_THREADS, 0, ctx->stream>>>(g);
+               else gather_columns_warp_kernel<PosT, false, 1><<<P.nchunks, GATHER_WARP_THREADS, 0, ctx->stream>>>(g); }
+    }
+    else gather_columns_kernel<PosT><<<P.nchunks, GATHER_THREADS, 0, ctx->stream>>>(g);
     LAUNCHED(ctx);
     EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -1790,6 +1798,7 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "fastpath")) { C->fast_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_closed_form")) { C->bary_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_v2")) { C->nl_version = value != 0 ? 3 : 1; return EXTFEM_OK; }
+    if (key && !strcmp(key, "gather_warp")) { C->gather_warp = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_kernel")) { C->nl_version = std::min(std::max(value, 1), 4); return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_prefetch_ctas")) { C->tmpl_ahead = value < 0 ? 0 : value; return EXTFEM_OK; }

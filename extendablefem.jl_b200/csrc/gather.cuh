@@ -91,6 +91,105 @@ gather_columns_kernel(const __grid_constant__ GatherArgs<PosT> g)
     for (int i = threadIdx.x; i < n; i += blockDim.x) g.nzval[base + i] = acc[i];
 }
 
+// The same reduction with the lanes of a warp on the ROWS of a cell-local column: the column (NRop contiguous doubles) and its
+// position bytes are read with one coalesced load each instead of 32 lanes walking 32 different cells.  A warp owns a run of at
+// most 32 consecutive columns of its CTA's chunk and streams through their (column, adjacent cell) pairs -- contiguous in the
+// adjacency arrays -- eight at a time, so the loads of a batch are in flight together; the column of a pair comes from a ballot
+// over the per-lane column ends (no search, no memory).  Pairs of one column are still added in ascending cell order: every sum
+// has the same order of additions as the thread-per-column kernel (bit-identical).  Columns of at most 16 rows are handled two
+// pairs at a time by the half warps.
+constexpr int GATHER_WARP_THREADS = 256;   // 8 warps: runs of at most 16 columns
+
+template <typename PosT, bool TR, int H>
+__global__ void __launch_bounds__(GATHER_WARP_THREADS, 3)
+gather_columns_warp_kernel(const __grid_constant__ GatherArgs<PosT> g)
+{
+    __shared__ double acc[GATHER_MAXNNZ];
+    const int k0 = g.chunkptr[blockIdx.x], k1 = g.chunkptr[blockIdx.x + 1];
+    const long long base = g.colptr[k0];
+    const int n = (int)(g.colptr[k1] - base);
+    int cb = 0;
+    while (cb + 1 < g.ncb && k0 >= g.coloff[cb + 1]) ++cb;
+    const int cloc = g.collocoff[cb];
+    if (cloc < 0) { // column block untouched by this operator
+        if (g.overwrite)
+            for (int i = threadIdx.x; i < n; i += blockDim.x) g.nzval[base + i] = 0.0;
+        return;
+    }
+    if (g.overwrite)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) acc[i] = 0.0;
+    else
+        for (int i = threadIdx.x; i < n; i += blockDim.x) acc[i] = g.nzval[base + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const PosT SENT = (PosT)~(PosT)0;
+    const long long *adjptr = g.adjptr[cb] - g.coloff[cb];      // indexed by the global column
+    const int *adjcell = g.adjcell[cb];
+    const unsigned char *adjloc = g.adjloc[cb];
+    const PosT *posmap = g.posmap[cb];
+    const int rstride = TR ? g.NRop : 1, cstride = TR ? 1 : g.NRop, CS = g.NCop * g.NRop;
+    const double scale = TR ? g.scale : 1.0;
+    constexpr int W = 32 / H;                                    // H pairs per warp step, W lanes per pair
+    const int sub = lane / W, tl = lane - sub * W;
+    constexpr int U = 8;
+    // this warp's run of columns (the chunk has at most GATHER_THREADS = 32 nw columns)
+    const int cpw = (k1 - k0 + nw - 1) / nw;
+    const int ka = min(k0 + warp * cpw, k1), kb = min(ka + cpw, k1);
+    const long long pend = lane < kb - ka ? adjptr[ka + lane + 1] : 0x7fffffffffffffffLL;
+    const int cbase = lane < kb - ka ? (int)(g.colptr[ka + lane] - base) : 0;
+    const long long P0 = adjptr[ka], P1 = adjptr[kb];
+    for (int t0 = 0; t0 < g.nrows_g; t0 += W) {
+        const bool on = t0 + tl < g.nrows_g;
+        const int rm = on ? g.rowmap[t0 + tl] : 0;
+        const double *lsrc = g.loc + (on ? g.rowsrc[t0 + tl] : 0) * rstride + cloc * cstride;
+        const PosT *pm = posmap + rm;
+        // (cell, local column) of the pairs one batch ahead of the value loads
+        int ncell[U], nkl[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long pp = P0 + u * H + sub;
+            ncell[u] = pp < P1 ? adjcell[pp] : 0;
+            nkl[u] = pp < P1 ? adjloc[pp] : 0;
+        }
+        for (long long p = P0; p < P1; p += U * H) {
+            int ab[U];
+            PosT pos[U];
+            double v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long pp = p + u * H + sub;
+                pos[u] = SENT; v[u] = 0.0; ab[u] = 0;
+                // column of the pair = number of columns of the run that end at or before it
+                int col = __popc(__ballot_sync(0xffffffffu, pend <= p + u * H));
+                if (H == 2) { const int col1 = __popc(__ballot_sync(0xffffffffu, pend <= p + u * H + 1)); col = sub ? col1 : col; }
+                ab[u] = __shfl_sync(0xffffffffu, cbase, min(col, 31));
+                if (pp < P1 && on) {
+                    pos[u] = pm[pp * g.NRpat];
+                    v[u] = lsrc[(long long)ncell[u] * CS + nkl[u] * cstride];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long pp = p + U * H + u * H + sub;
+                ncell[u] = pp < P1 ? adjcell[pp] : 0;
+                nkl[u] = pp < P1 ? adjloc[pp] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double w = TR ? scale * v[u] : v[u];
+                if (H == 2) {
+                    if (sub == 0 && pos[u] != SENT) acc[ab[u] + pos[u]] += w;
+                    __syncwarp();
+                    if (sub == 1 && pos[u] != SENT) acc[ab[u] + pos[u]] += w;
+                } else if (pos[u] != SENT) acc[ab[u] + pos[u]] += w;
+                __syncwarp();              // another lane may own the same row in the next cell
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) g.nzval[base + i] = acc[i];
+}
+
 struct GatherVecArgs {
     int nrb;
     long long rowoff[MAXBLOCKS + 1];

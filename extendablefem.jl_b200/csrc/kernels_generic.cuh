@@ -920,7 +920,7 @@ __device__ __forceinline__ void nl_apply_fixed(int id, const double (&u)[NIO], c
 }
 
 template <int DIM, int NIO>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tables T, double *__restrict__ wJ, double *__restrict__ rqg)
 {
     extern __shared__ __align__(16) unsigned char tb[];
