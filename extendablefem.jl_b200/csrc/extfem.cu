@@ -73,6 +73,8 @@ struct TemplatePlan {
     long long vol_version = -1;
     std::vector<JitTemplate> jtmpl;  // host copy of the templates (plan-time specialisation, jit.cuh)
     std::unique_ptr<JitModule> jit;
+    DevBuf walk_live[2], walk_next;  // persistent walk kernel: launch-order warps of the short / long class, queue heads
+    int walk_nlive[2] = {0, 0}, walk_doubles[2] = {0, 0}, walk_nl = 1, walk_ns = 0, walk_ctas = 1;
     DevBuf jit_live[2];              // launch-order warps of the short- / long-column class
     int jit_nlive[2] = {0, 0};
     DevBuf walk;                     // walk records of the templates (walkplan.h), [nrounds][TW_RW] words, same round indices
@@ -135,6 +137,10 @@ struct Ctx {
     DevBuf nlpt;                // w J and (J u - F) per (cell, quadrature point) of the tensor-core nonlinear path
     bool tmpl_enabled = true;   // option "fastpath_templates": 0 keeps every column on the record kernel
     int tmpl_ahead = 1024;      // option "template_prefetch_ctas": CTAs ahead whose start-up data is prefetched into L2
+    int sm_count = 148;
+    int tmpl_walk_roles = 0;       // option "template_walk_roles": 10 nl + ns forces the long / short warps of a persistent CTA (0: modelled)
+    int tmpl_persistent = 0;       // option "template_persistent": N > 0 runs the walk kernel as persistent CTAs (at most N per SM) fed from
+                                   // two queues; measured slower than one CTA per 4 groups in the release build (profiles/r02_tuning_log.md)
     int tmpl_pool = TP_POOL_BYTES; // option "template_pool_bytes": shared-memory pool of one template CTA
     bool jit_enabled = false;   // option "template_jit": plan-time specialisation of the templates (jit.cuh); off by default
     long long jit_mincols = 200000; // option "template_jit_min_cols": smallest column block that is worth the compile time
@@ -952,6 +958,53 @@ static int build_template_plan(Ctx *ctx, Pattern &P, int b, int ns)
                 T.walk_ok = true;
             }
         }
+        if (T.walk_ok) {
+            // persistent walk kernel: the column groups are split by length into a short and a long class; a CTA has nl warps with
+            // an accumulator area for the longest group (they serve the long queue, then the short one) and ns warps with a short
+            // area.  Split and (nl, ns) maximise the modelled throughput: work = rounds + a per-group constant, every warp slot the
+            // shared memory admits is busy until the queues are empty.
+            std::map<int, std::pair<long long, int>> byL;        // L -> (work, groups)
+            for (size_t i = 0; i < launch.size(); ++i)
+                if (tp_desc_m(launch[i].y) > 0) { auto &e = byL[tp_desc_L(launch[i].y)]; e.first += tp_desc_m(launch[i].y) + 2; ++e.second; }
+            auto area = [](int L) { return (L * TP_LD + 32 + 1) & ~1; };   // accumulators + column pointers (records are in the constant bank)
+            const int Lmax = byL.empty() ? 1 : byL.rbegin()->first;
+            double best = 1e300;
+            int bsplit = Lmax, bnl = 1, bns = 0, bctas = 1;
+            for (auto &cand : byL) {
+                const int Ls = cand.first;
+                double wS = 0, wL = 0;
+                for (auto &kv : byL) (kv.first <= Ls ? wS : wL) += (double)kv.second.first;
+                const double aS = area(Ls) * 8.0, aL = area(Lmax) * 8.0;
+                for (int nl = 1; nl <= 4; ++nl)
+                    for (int ns = 0; ns + nl <= 8; ++ns) {
+                        if (Ls == Lmax && ns > 0) continue;      // one class only
+                        if (ctx->tmpl_walk_roles > 0 && (nl != ctx->tmpl_walk_roles / 10 || ns != ctx->tmpl_walk_roles % 10)) continue;
+                        const int w = nl + ns;
+                        const int ctas = std::min({(int)((227.0 * 1024) / (nl * aL + ns * aS + 1024)), 24 / w, ctx->tmpl_persistent});
+                        if (ctas < 1) continue;
+                        const double nL = nl * ctas, nS = ns * ctas;
+                        double t = wL / nL;
+                        if (!(nS > 0 && wS / nS <= t)) t += (wS - nS * t) / (nL + nS);
+                        if (t < best) { best = t; bsplit = Ls; bnl = nl; bns = ns; bctas = ctas; }
+                    }
+            }
+            std::vector<int> q[2];
+            for (size_t i = 0; i < launch.size(); ++i)
+                if (tp_desc_m(launch[i].y) > 0) q[tp_desc_L(launch[i].y) > bsplit ? 1 : 0].push_back((int)i);
+            T.walk_doubles[0] = area(bsplit); T.walk_doubles[1] = area(Lmax);
+            T.walk_nl = bnl; T.walk_ns = bns; T.walk_ctas = bctas;
+            for (int c = 0; c < 2; ++c) {
+                T.walk_nlive[c] = (int)q[c].size();
+                if (int rc = upload(ctx, T.walk_live[c], q[c].empty() ? (const int *)&c : q[c].data(), std::max<size_t>(q[c].size(), 1) * 4)) return rc;
+            }
+            if (int rc = ensure(ctx, T.walk_next, 8)) return rc;
+            if (getenv("EXTFEM_VERBOSE")) {
+                fprintf(stderr, "extfem: walk queues short %d (L <= %d, area %d doubles) long %d (area %d doubles); CTA = %d long + %d short warps, %d per SM; "
+                        "column lengths (groups):", T.walk_nlive[0], bsplit, T.walk_doubles[0], T.walk_nlive[1], T.walk_doubles[1], bnl, bns, bctas);
+                for (auto &kv : byL) fprintf(stderr, " %d:%d", kv.first, kv.second.second);
+                fprintf(stderr, "\n");
+            }
+        }
         std::vector<int> live[2];
         for (size_t i = 0; i < launch.size(); ++i)
             if (tp_desc_m(launch[i].y) > 0) live[tp_desc_L(launch[i].y) > JIT_SPLIT_L ? 1 : 0].push_back((int)i);
@@ -1143,9 +1196,24 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
         A.wdesc = T.wdesc.as<int4>(); A.slotpb = T.slotpb.as<int>(); A.slotptr = T.slotptr.as<double *>();
         A.tmpl = T.walk.as<unsigned>(); A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
         A.nwarps = T.nctas * TP_MAXW; A.ahead = ctx->tmpl_ahead * TP_MAXW; A.classmask = ctx->tmpl_classmask;
-        auto k = first ? tw_gather_kernel<true> : tw_gather_kernel<false>;
-        if (int rc = smem_attr(ctx, (const void *)k, 227 * 1024)) return rc;
-        k<<<T.nctas, TP_MAXW * 32, T.pool_bytes, ctx->stream>>>(A);
+        if (ctx->tmpl_persistent && ctx->tmpl_classmask == 3 && T.walk_nlive[0] + T.walk_nlive[1] > 0) {
+            // persistent CTAs: tmpl_persistent CTAs per SM (limited by the accumulator areas), the warps take groups from two queues
+            auto k = first ? tw_gather_persistent_kernel<true> : tw_gather_persistent_kernel<false>;
+            if (int rc = smem_attr(ctx, (const void *)k, 227 * 1024)) return rc;
+            TWQueues Q;
+            for (int c = 0; c < 2; ++c) { Q.live[c] = T.walk_live[c].as<int>(); Q.n[c] = T.walk_nlive[c]; Q.doubles[c] = T.walk_doubles[c]; }
+            Q.next = T.walk_next.as<int>();
+            EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(Q.next, 0, 8, ctx->stream));
+            Q.nlong = T.walk_nl;
+            const int w = T.walk_nl + T.walk_ns;
+            const size_t smem = (size_t)(T.walk_nl * T.walk_doubles[1] + T.walk_ns * T.walk_doubles[0]) * 8;
+            const int grid = std::min((T.walk_nlive[0] + T.walk_nlive[1] + w - 1) / w, ctx->sm_count * T.walk_ctas);
+            k<<<grid, w * 32, smem, ctx->stream>>>(A, Q);
+        } else {
+            auto k = first ? tw_gather_kernel<true> : tw_gather_kernel<false>;
+            if (int rc = smem_attr(ctx, (const void *)k, 227 * 1024)) return rc;
+            k<<<T.nctas, TP_MAXW * 32, T.pool_bytes, ctx->stream>>>(A);
+        }
         LAUNCHED(ctx);
         EXTFEM_CUDA_CHECK(ctx, cudaGetLastError());
         walk_done = true;
@@ -1717,6 +1785,7 @@ int extfem_ctx_create(int device, extfem_ctx **out)
         delete C;
         return fail(nullptr, EXTFEM_ERR_CUDA, "cannot initialise device");
     }
+    if (cudaDeviceGetAttribute(&C->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || C->sm_count <= 0) C->sm_count = 148;
     for (auto &ev : C->ev) cudaEventCreate(&ev);
     for (auto &ev : C->uev) cudaEventCreate(&ev);
     cudaStreamCreateWithFlags(&C->stream2, cudaStreamNonBlocking);
@@ -1802,6 +1871,8 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "nonlinear_kernel")) { C->nl_version = std::min(std::max(value, 1), 4); return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_prefetch_ctas")) { C->tmpl_ahead = value < 0 ? 0 : value; return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_walk_roles")) { C->tmpl_walk_roles = std::max(value, 0); return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_persistent")) { C->tmpl_persistent = std::min(std::max(value, 0), 16); return EXTFEM_OK; }
     if (key && !strcmp(key, "template_pool_bytes")) { C->tmpl_pool = std::min(std::max(value, 4096), 200 * 1024); return EXTFEM_OK; }
     if (key && !strcmp(key, "template_jit")) { C->jit_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_jit_min_cols")) { C->jit_mincols = value < 0 ? 0 : value; return EXTFEM_OK; }

@@ -1,4 +1,6 @@
-"""Summary of ncu CSV pages exported by scripts/gpu_nl_ncufull.sh: python scripts/ncu_csv_summary.py <prefix> [ncells]"""
+"""Summary of the ncu CSV pages (`ncu -i x.ncu-rep --page raw|source --csv`, exported on the GPU box by scripts/gpu_final*.sh
+because the reports exceed the transfer limit): key metrics, instruction share / stall-sample share of the SASS regions, opcode
+histogram.  usage: python profiles/ncu_csv_summary.py <prefix> [work items for per-item instruction counts] > profiles/rNN_x.txt"""
 import csv
 import sys
 
@@ -34,3 +36,13 @@ for s in seg:
 top = sorted(range(len(src)), key=lambda i: -int(src[i][2]))[:14]
 for i in sorted(top):
     print(i, src[i][1].strip()[:80], src[i][5], src[i][2])
+
+import collections
+op = collections.Counter()
+for r in src:
+    toks = r[1].split()
+    if not toks:
+        continue
+    o = (toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]).split(".")[0]
+    op[o] += int(r[5])
+print("opcode histogram (warp-level executed):", ", ".join(f"{k} {v}" for k, v in op.most_common(24)))
