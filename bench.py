@@ -286,40 +286,71 @@ def run_ours(args):
                         "entries_checked": sum(x["entries_checked"] for x in gathered), "columns_checked": sum(x["columns_checked"] for x in gathered),
                         "against": gathered[0]["against"]}
 
-    # ---- e2e through the C-ABI with HOST buffers: H2D of the coordinates (pinned), D2H of nzval and b
+    # ---- e2e through the C-ABI with HOST buffers: H2D of the coordinates (pinned), D2H of the matrix values and b.
+    # The form is symmetric, so the headline variant ships the LOWER TRIANGLE (extfem_values_get_lower: the suffix of every sorted
+    # column, packed on the device; the caller wraps it as Symmetric(A, :L)); the full copy-back is timed beside it.
     coords_h = torch.from_numpy(np.ascontiguousarray(grid.coords)).pin_memory()
+    nnz_lower = eng.pattern_get_lower(pat, want_rowval=False)[0]
     nz_h = torch.empty(nnz, dtype=torch.float64).pin_memory()
+    lz_h = torch.empty(nnz_lower, dtype=torch.float64).pin_memory()
     b_h = torch.empty(nrows, dtype=torch.float64).pin_memory()
     vol_h = torch.from_numpy(np.ascontiguousarray(sh.cellvolumes)).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
 
-    def step_e2e():
+    def step_e2e(lower):
         eng.mesh_update_coords(mesh, coords_h, vol_h)
+        eng.assemble_bilinear(pat, lap)
         if world > 1:
-            eng.assemble_bilinear(pat, lap)
             eng.dist_reduce_system(pat, True, False)
-            eng.assemble_linear(pat, rhs)
+        eng.assemble_linear(pat, rhs)
+        if world > 1:
             eng.dist_reduce_system(pat, False, True)
-            eng.values_get(pat, nzval_out=nz_h, b_out=b_h)
+        if lower:
+            eng.values_get_lower(pat, nzval_out=lz_h, b_out=b_h)
         else:
-            eng.assemble_bilinear(pat, lap, nzval_out=nz_h)
-            eng.assemble_linear(pat, rhs, b_out=b_h)
+            eng.values_get(pat, nzval_out=nz_h, b_out=b_h)
 
-    step_e2e()
-    barrier()
-    eng.event_record(2)
-    for _ in range(e2e_steps):
-        step_e2e()
-    eng.event_record(3)
-    ms_e2e = eng.event_elapsed_ms(2, 3) / e2e_steps
-    barrier()
+    def time_e2e(lower):
+        step_e2e(lower)
+        barrier()
+        eng.event_record(2)
+        for _ in range(e2e_steps):
+            step_e2e(lower)
+        eng.event_record(3)
+        ms = eng.event_elapsed_ms(2, 3) / e2e_steps
+        barrier()
+        return ms
+
+    ms_e2e_full = time_e2e(False)
+    ms_e2e = time_e2e(True)
     checksum = float(nz_h.sum())   # stiffness matrix annihilates constants: sum of all entries ~ 0 (single GPU)
 
+    # ---- device-resident solve (the path north_star describes): coordinates in, assemble, penalties, Jacobi-CG to 1e-10 on the
+    # GPU, only x back (single GPU; config 5 is the multi-GPU version of this)
+    resident = None
+    if world == 1 and not args.no_parity:
+        xyz = FES.dof_coordinates()
+        onb = np.nonzero((xyz == 0.0).any(axis=1) | (xyz == 1.0).any(axis=1))[0] + 1
+        torch.cuda.synchronize(); eng.synchronize()
+        t0 = time.perf_counter()
+        eng.mesh_update_coords(mesh, coords_h, vol_h)
+        eng.assemble_bilinear(pat, lap)
+        eng.assemble_linear(pat, rhs)
+        eng.apply_penalties(pat, onb, None, 1e30)
+        eng.synchronize()
+        t1 = time.perf_counter()
+        xs, its, rr = eng.cg(pat, rtol=1e-10, maxit=5000)
+        t2 = time.perf_counter()
+        resident = {"ms_coords_in_to_system_ready": (t1 - t0) * 1e3, "cg_iterations": int(its), "relres": float(rr), "ms_cg": (t2 - t1) * 1e3,
+                    "ms_total": (t2 - t0) * 1e3, "h2d_bytes": int(coords_h.numel() * 8 + vol_h.numel() * 8 + onb.size * 8), "d2h_bytes": int(nrows * 8),
+                    "max_abs_solution": float(np.abs(xs).max()),
+                    "note": "homogeneous Dirichlet data on the cube boundary by penalties, Jacobi-CG until |r| <= 1e-10 |r0|; wall clock"}
+
     ms_step = ms_total / args.steps
-    t = torch.tensor([ms_step, ms_e2e], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_step, ms_e2e, ms_e2e_full], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, ms_e2e = float(t[0]), float(t[1])
+    ms_step, ms_e2e, ms_e2e_full = float(t[0]), float(t[1]), float(t[2])
     nz_layers = args.n * world if args.scaling == "weak" else args.n
     cells_total = 6 * args.n * args.n * nz_layers
     value = cells_total / (ms_step * 1e-3)
@@ -364,7 +395,13 @@ def run_ours(args):
                          "algorithmic_bytes": alg, "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(coords_h.numel() * 8 + vol_h.numel() * 8),
-                    "d2h_bytes_per_step": int(nz_h.numel() * 8 + b_h.numel() * 8)},
+                    "d2h_bytes_per_step": int(lz_h.numel() * 8 + b_h.numel() * 8),
+                    "variant": "C-ABI calls with pinned host buffers: coordinates + volumes in, lower triangle of the symmetric matrix "
+                               "(extfem_values_get_lower) + rhs out"},
+            "e2e_variants": {"full_copy_back": {"value": cells_total / (ms_e2e_full * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_full,
+                                                "d2h_bytes_per_step": int(nz_h.numel() * 8 + b_h.numel() * 8),
+                                                "variant": "every matrix value + rhs out (extfem_values_get)"},
+                             "resident_solve": resident},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "setup_s": {"mesh_host": t_mesh, "upload_adjacency_pattern": t_setup},

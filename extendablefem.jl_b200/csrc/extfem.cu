@@ -94,6 +94,8 @@ struct Pattern {
     int poswidth = 1;                          // bytes per posmap entry
     int maxcollen = 0;
     DevBuf colptr, rowval, nzval, b;
+    DevBuf lstart, lcolptr, lpack;             // lower-triangle export (extfem_values_get_lower): suffix starts, packed colptr, staging
+    long long nnz_lower = -1;
     std::vector<std::unique_ptr<DevBuf>> posmap; // per column block
     DevBuf chunkptr;
     int nchunks = 0;
@@ -2532,6 +2534,72 @@ int extfem_values_get(extfem_ctx *ctx, int pattern, double *nzval, double *b)
     CTX_GUARD(ctx);
     GET_PATTERN(pattern);
     if (nzval) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(nzval, P.nzval.p, (size_t)P.nnz * 8, cudaMemcpyDefault, C->stream));
+    if (b) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    return EXTFEM_OK;
+}
+
+// suffix starts and packed column pointers of the lower triangle, once per pattern
+static int ensure_lower(Ctx *C, Pattern &P)
+{
+    if (P.nnz_lower >= 0) return EXTFEM_OK;
+    if (!P.square || P.nrows != P.ncols) return fail(C, EXTFEM_ERR_BAD_ARGUMENT, "the lower triangle needs a square pattern");
+    DevBuf cnt, tmp;
+    if (int rc = ensure(C, P.lstart, (size_t)P.ncols * 8)) return rc;
+    if (int rc = ensure(C, P.lcolptr, (size_t)(P.ncols + 1) * 8)) return rc;
+    if (int rc = ensure(C, cnt, (size_t)(P.ncols + 1) * 8)) return rc;
+    EXTFEM_CUDA_CHECK(C, cudaMemsetAsync(cnt.p, 0, (size_t)(P.ncols + 1) * 8, C->stream));
+    lower_start_kernel<<<nblocks(P.ncols, 256), 256, 0, C->stream>>>(P.ncols, P.colptr.as<long long>(), P.rowval.as<int>(), P.lstart.as<long long>(),
+                                                                   cnt.as<long long>());
+    LAUNCHED(C);
+    size_t tb = 0;
+    EXTFEM_CUDA_CHECK(C, cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.as<long long>(), P.lcolptr.as<long long>(), (int)(P.ncols + 1), C->stream));
+    if (int rc = ensure(C, tmp, tb)) return rc;
+    EXTFEM_CUDA_CHECK(C, cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.as<long long>(), P.lcolptr.as<long long>(), (int)(P.ncols + 1), C->stream));
+    LAUNCHED(C);
+    long long n = 0;
+    EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(&n, P.lcolptr.as<long long>() + P.ncols, 8, cudaMemcpyDeviceToHost, C->stream));
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    P.nnz_lower = n;
+    return EXTFEM_OK;
+}
+
+int extfem_pattern_get_lower(extfem_ctx *ctx, int pattern, int64_t *nnz_lower, int64_t *colptr, int64_t *rowval)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (int rc = ensure_lower(C, P)) return rc;
+    if (nnz_lower) *nnz_lower = P.nnz_lower;
+    DevBuf c64, r64;
+    if (colptr) {
+        if (int rc = ensure(C, c64, (size_t)(P.ncols + 1) * 8)) return rc;
+        add_one_kernel<<<nblocks(P.ncols + 1, 256), 256, 0, C->stream>>>(P.ncols + 1, P.lcolptr.as<long long>(), c64.as<long long>());
+        LAUNCHED(C);
+        EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(colptr, c64.p, (size_t)(P.ncols + 1) * 8, cudaMemcpyDefault, C->stream));
+    }
+    if (rowval) {
+        if (int rc = ensure(C, r64, (size_t)std::max<long long>(P.nnz_lower, 1) * 8)) return rc;
+        lower_pack_kernel<int, long long><<<nblocks(P.ncols * 32, 256), 256, 0, C->stream>>>(P.ncols, P.lstart.as<long long>(), P.lcolptr.as<long long>(),
+                                                                                           P.rowval.as<int>(), r64.as<long long>(), 1LL);
+        LAUNCHED(C);
+        EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(rowval, r64.p, (size_t)P.nnz_lower * 8, cudaMemcpyDefault, C->stream));
+    }
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
+    return EXTFEM_OK;
+}
+
+int extfem_values_get_lower(extfem_ctx *ctx, int pattern, double *nzval_lower, double *b)
+{
+    CTX_GUARD(ctx);
+    GET_PATTERN(pattern);
+    if (int rc = ensure_lower(C, P)) return rc;
+    if (nzval_lower) {
+        if (int rc = ensure(C, P.lpack, (size_t)std::max<long long>(P.nnz_lower, 1) * 8)) return rc;
+        lower_pack_kernel<double, double><<<nblocks(P.ncols * 32, 256), 256, 0, C->stream>>>(P.ncols, P.lstart.as<long long>(), P.lcolptr.as<long long>(),
+                                                                                           P.nzval.as<double>(), P.lpack.as<double>(), 0.0);
+        LAUNCHED(C);
+        EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(nzval_lower, P.lpack.p, (size_t)P.nnz_lower * 8, cudaMemcpyDefault, C->stream));
+    }
     if (b) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
     EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
     return EXTFEM_OK;

@@ -210,4 +210,38 @@ __global__ void csc_export_kernel(const long long *__restrict__ colptr, long lon
     if (rowval_out && i < nnz) rowval_out[i] = (long long)rowval[i] + 1;
 }
 
+// ---- lower triangle of a square CSC matrix (rows sorted per column: the entries with row >= column are a SUFFIX of the column) --
+// lstart[j] = index of the first entry of column j with row >= j; lcount[j] = entries from there to the end of the column
+__global__ void lower_start_kernel(long long ncols, const long long *__restrict__ colptr, const int *__restrict__ rowval,
+                                   long long *__restrict__ lstart, long long *__restrict__ lcount)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    long long lo = colptr[j], hi = colptr[j + 1];
+    const long long end = hi;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (rowval[mid] < j) lo = mid + 1; else hi = mid;
+    }
+    lstart[j] = lo; lcount[j] = end - lo;
+}
+
+// one warp per column: out[lcolptr[j] + k] = src[lstart[j] + k]  (values: T = double; row indices: int -> 1-based int64)
+template <typename TI, typename TO>
+__global__ void lower_pack_kernel(long long ncols, const long long *__restrict__ lstart, const long long *__restrict__ lcolptr,
+                                  const TI *__restrict__ src, TO *__restrict__ out, TO add)
+{
+    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= ncols) return;
+    const long long s = lstart[j], o = lcolptr[j], n = lcolptr[j + 1] - o;
+    for (long long k = lane; k < n; k += 32) out[o + k] = (TO)src[s + k] + add;
+}
+
+__global__ void add_one_kernel(long long n, const long long *__restrict__ in, long long *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] + 1;
+}
+
 } // namespace extfem

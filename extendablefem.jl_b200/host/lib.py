@@ -28,6 +28,7 @@ EXPORTS = [
     "extfem_dist_unique_id", "extfem_dist_init", "extfem_dist_set_interfaces", "extfem_dist_sum_rhs", "extfem_dist_spmv", "extfem_dist_cg",
     "extfem_mesh_set_bfaces", "extfem_space_set_bfacedofs", "extfem_integrate", "extfem_values_zero", "extfem_apply_values",
     "extfem_dist_set_owned", "extfem_dist_reduce_system", "extfem_dist_spmv_owned", "extfem_dist_cg_owned",
+    "extfem_pattern_get_lower", "extfem_values_get_lower",
 ]
 
 
@@ -285,6 +286,27 @@ class Engine:
         b = b_out if b_out is not None else (np.empty(nrows) if want_b else None)
         self._check(self.lib.extfem_values_get(self.ctx, pattern, _p(nz), _p(b)))
         return nz, b
+
+    def pattern_get_lower(self, pattern: int, want_rowval=True):
+        """Pattern of the lower triangle (Int64, 1-based): (nnz_lower, colptr, rowval)."""
+        _, ncols, _ = self.pattern_dims(pattern)
+        n = C.c_int64(0)
+        self._check(self.lib.extfem_pattern_get_lower(self.ctx, pattern, C.byref(n), None, None))
+        colptr = np.empty(ncols + 1, np.int64)
+        rowval = np.empty(n.value, np.int64) if want_rowval else None
+        self._check(self.lib.extfem_pattern_get_lower(self.ctx, pattern, None, _p(colptr), _p(rowval)))
+        return int(n.value), colptr, rowval
+
+    def values_get_lower(self, pattern, nzval_out=None, b_out=None, want_b=True):
+        """Lower triangle of the device-resident (symmetric) matrix, packed in column order, and the rhs."""
+        nrows, _, _ = self.pattern_dims(pattern)
+        if nzval_out is None:
+            n = C.c_int64(0)
+            self._check(self.lib.extfem_pattern_get_lower(self.ctx, pattern, C.byref(n), None, None))
+            nzval_out = np.empty(n.value)
+        b = b_out if b_out is not None else (np.empty(nrows) if want_b else None)
+        self._check(self.lib.extfem_values_get_lower(self.ctx, pattern, _p(nzval_out), _p(b)))
+        return nzval_out, b
 
     def values_set(self, pattern, nzval=None, b=None):
         self._check(self.lib.extfem_values_set(self.ctx, pattern, _p(nzval), _p(b)))

@@ -10,7 +10,7 @@
 # closure with the same call shape that ADDS the operator's contribution into the arrays it is handed -- exactly what the
 # reference closure does -- so `solve`, `ProblemDescription`, `assign_operator!` and `assemble_system!` stay untouched.
 module ExtFEMCuda
-using ExtendableFEM, ExtendableFEMBase, ExtendableGrids, SparseArrays
+using ExtendableFEM, ExtendableFEMBase, ExtendableGrids, SparseArrays, LinearAlgebra
 const lib = "libextfem_cuda"            # extendablefem.jl_b200/csrc/libextfem_cuda.so on LD_LIBRARY_PATH
 
 # ---- mirror of `extfem_opdesc` (include/extfem_cuda.h); NTuple{4,Int32} == int32_t[EXTFEM_MAXARGS] -----------------------
@@ -278,5 +278,16 @@ end
 function values_get!(A::FEMatrix, b::FEVector, gs)
     check(gs.ctx.ptr, ccall((:extfem_values_get, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}),
                             gs.ctx.ptr, gs.pattern, A.entries.cscmatrix.nzval, b.entries))
+end
+# symmetric forms: only the lower triangle crosses PCIe (half the bytes); the result is what CHOLMOD / cg take of an SPD matrix
+function lower_system(gs, b::Vector{Float64})
+    n = Ref{Int64}(0)
+    sig = (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Int64})
+    check(gs.ctx.ptr, ccall((:extfem_pattern_get_lower, lib), Cint, sig, gs.ctx.ptr, gs.pattern, n, C_NULL, C_NULL))
+    colptr = Vector{Int64}(undef, gs.nrows + 1); rowval = Vector{Int64}(undef, n[]); nzval = Vector{Float64}(undef, n[])
+    check(gs.ctx.ptr, ccall((:extfem_pattern_get_lower, lib), Cint, sig, gs.ctx.ptr, gs.pattern, C_NULL, colptr, rowval))
+    check(gs.ctx.ptr, ccall((:extfem_values_get_lower, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}),
+                            gs.ctx.ptr, gs.pattern, nzval, b))
+    return Symmetric(SparseMatrixCSC(gs.nrows, gs.nrows, colptr, rowval, nzval), :L)
 end
 end # module

@@ -231,6 +231,12 @@ int extfem_integrate(extfem_ctx *ctx, int pattern, const extfem_opdesc *op, cons
 int extfem_values_zero(extfem_ctx *ctx, int pattern, int zero_matrix, int zero_rhs);
 int extfem_values_get(extfem_ctx *ctx, int pattern, double *nzval /*NULL ok*/, double *b /*NULL ok*/);
 int extfem_values_set(extfem_ctx *ctx, int pattern, const double *nzval /*NULL ok*/, const double *b /*NULL ok*/);
+/* Symmetric forms: only the lower triangle crosses PCIe (half the bytes of extfem_values_get).  Rows are sorted per column, so
+ * the entries with row >= column are a suffix of every column; they are packed on the device in column order.  The Julia side
+ * wraps the result as Symmetric(SparseMatrixCSC(n, n, colptr, rowval, nzval), :L) -- what CHOLMOD / a CG need of an SPD matrix.
+ * pattern_get_lower: nnz_lower, colptr [ncols+1] and rowval [nnz_lower] (Int64, 1-based; any of them may be NULL).           */
+int extfem_pattern_get_lower(extfem_ctx *ctx, int pattern, int64_t *nnz_lower, int64_t *colptr, int64_t *rowval);
+int extfem_values_get_lower(extfem_ctx *ctx, int pattern, double *nzval_lower /*[nnz_lower], NULL ok*/, double *b /*NULL ok*/);
 /* raw device pointers (colptr int64 0-based, rowval int32 0-based, nzval, b) for zero-copy users */
 int extfem_device_ptrs(extfem_ctx *ctx, int pattern, void **colptr, void **rowval, void **nzval, void **b);
 /* apply_penalties! (homogeneousdata_operator.jl:186-201): A[d,d] = penalty, b[d] = penalty*value[d].  On a sharded system

@@ -335,3 +335,29 @@ def test_apply_values_and_zero(pkg, ora, engine):
     dofs = np.array([1, 5, S.N])
     engine.apply_values(dofs, np.array([7.0, 8.0, 9.0]), sol)
     assert sol[0] == 7.0 and sol[4] == 8.0 and sol[-1] == 9.0 and sol[1] == 1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["p2_3d", "stokes2d"])
+def test_lower_triangle_export(pkg, ora, engine, case):
+    """extfem_pattern_get_lower / extfem_values_get_lower: the packed lower triangle (pattern Int64 1-based, values, rhs) equals
+    scipy's tril of the full matrix -- scalar P2 in 3D and a 2-block (velocity, pressure) system."""
+    import scipy.sparse as sp
+    if case == "p2_3d":
+        X = np.linspace(0, 1, 6)
+        S = System(pkg, ora, engine, pkg.simplexgrid(X, X, X), [pkg.H1P2(1, 3)])
+        engine.assemble_bilinear(S.pat, engine.make_opdesc([(0, GRAD)], [(0, GRAD)], factor=1.3))
+    else:
+        X = np.linspace(0, 1, 9)
+        S = System(pkg, ora, engine, pkg.simplexgrid(X, X), [pkg.H1P2(2, 2), pkg.H1P1(1)])
+        t = [(0, GRAD), (1, ID)]
+        engine.assemble_bilinear(S.pat, engine.make_opdesc(t, t, kernel_id=pkg.lib.kernel_id("stokes"), params=[0.1]))
+    engine.assemble_linear(S.pat, engine.make_opdesc([(0, ID)], kernel_id=pkg.lib.kernel_id("constant_one")))
+    nz, b = engine.values_get(S.pat)
+    A = sp.csc_matrix((nz, S.rowval - 1, S.colptr - 1), shape=(S.N, S.N))
+    L = sp.tril(A, format="csc")
+    # structural zeros of the pattern survive in A (explicit entries), tril keeps them
+    n, cp, rv = engine.pattern_get_lower(S.pat)
+    assert n == L.nnz and np.array_equal(cp - 1, L.indptr) and np.array_equal(rv - 1, L.indices)
+    lz, lb = engine.values_get_lower(S.pat)
+    assert np.array_equal(lz, L.data) and np.array_equal(lb, b)
