@@ -367,7 +367,7 @@ static bool kernel_known(int kind, int id)
     if (kind == KIND_BILINEAR) return id >= EXTFEM_BLK_STANDARD && id <= EXTFEM_BLK_ROBIN108;
     if (kind == KIND_LINEAR) return id >= EXTFEM_LIN_CONSTANT_ONE && id <= EXTFEM_LIN_STEP105;
     if (kind == KIND_INTEGRATE) return id >= EXTFEM_II_STANDARD && id <= EXTFEM_II_L2ERR_EXP108;
-    return id >= EXTFEM_NL_NSE2D && id <= EXTFEM_NL_STVENANT230;
+    return id >= EXTFEM_NL_NSE2D && id <= EXTFEM_NL_POROUS106;
 }
 
 static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const double *sol, Prepared &R)
@@ -535,6 +535,8 @@ static int prepare(Ctx *ctx, Pattern &P, const extfem_opdesc *d, int kind, const
     if (kind == KIND_NONLINEAR && (d->kernel_id == EXTFEM_NL_RCD || d->kernel_id == EXTFEM_NL_NLPOISSON105) &&
         (off_g != 1 + M.dim || off_t != 1 + M.dim || (d->kernel_id == EXTFEM_NL_NLPOISSON105 && d->nparams < 1)))
         return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "rcd / nlpoisson105 need [id(u), grad(u)] of a scalar unknown");
+    if (kind == KIND_NONLINEAR && d->kernel_id == EXTFEM_NL_POROUS106 && (off_g != 1 + M.dim || off_t != M.dim || d->nparams < 1))
+        return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "porous106 needs test [grad(u)], args [id(u), grad(u)] of a scalar unknown and params m");
     if (kind == KIND_BILINEAR && d->kernel_id == EXTFEM_BLK_ROBIN108 && (d->nparams < 1 || off_t != off_a))
         return fail(ctx, EXTFEM_ERR_BAD_ARGUMENT, "robin108 needs params g and equal operator lengths");
     if (sol) {
@@ -1847,7 +1849,7 @@ int extfem_kernel_id(const char *name)
         {"constant_one", EXTFEM_LIN_CONSTANT_ONE}, {"constant_params", EXTFEM_LIN_CONSTANT_PARAMS}, {"xy", EXTFEM_LIN_XY},
         {"sincos301", EXTFEM_LIN_SINCOS301}, {"tabulated", EXTFEM_LIN_TABULATED}, {"exp2x", EXTFEM_LIN_EXP2X}, {"step105", EXTFEM_LIN_STEP105},
         {"nse2d", EXTFEM_NL_NSE2D}, {"nl_linnse7", EXTFEM_NL_LINNSE7}, {"neohooke3d", EXTFEM_NL_NEOHOOKE3D}, {"rcd", EXTFEM_NL_RCD},
-        {"nlpoisson105", EXTFEM_NL_NLPOISSON105}, {"stvenant230", EXTFEM_NL_STVENANT230},
+        {"nlpoisson105", EXTFEM_NL_NLPOISSON105}, {"stvenant230", EXTFEM_NL_STVENANT230}, {"porous106", EXTFEM_NL_POROUS106},
         {"ii_standard", EXTFEM_II_STANDARD}, {"l2norm", EXTFEM_II_L2NORM}, {"l2diff_tabulated", EXTFEM_II_L2DIFF_TABULATED},
         {"l2err_sincos301", EXTFEM_II_L2ERR_SINCOS301}, {"l2err_exp108", EXTFEM_II_L2ERR_EXP108}};
     if (name)

@@ -244,6 +244,16 @@ __device__ __forceinline__ void nl_apply(int id, int dim, const double *in, cons
 #pragma unroll
         for (int d = 0; d < dim; ++d) { val[1 + d] = p[0] * in[1 + d]; J[(1 + d) * nin + 1 + d] = p[0]; }
     } break;
+    case EXTFEM_NL_POROUS106: {
+        // porous medium flux m u^(m-1) grad u (result has dim components, input u and grad u)
+        const double m = p[0], um1 = pow(in[0], m - 1.0), um2 = (m == 2.0) ? 1.0 : pow(in[0], m - 2.0);
+#pragma unroll
+        for (int d = 0; d < dim; ++d) {
+            val[d] = m * um1 * in[1 + d];
+            J[d * nin + 0] = m * (m - 1.0) * um2 * in[1 + d];
+            J[d * nin + 1 + d] = m * um1;
+        }
+    } break;
     case EXTFEM_NL_STVENANT230: {
         // Green-Lagrange strain (Voigt) minus thermal strain, isotropic Hooke; material by cell region
         const int R = (int)p[0], m = region >= 1 && region <= R ? region - 1 : 0;

@@ -91,8 +91,9 @@ enum { /* NonlinearOperator kernels with analytic Jacobians */
     EXTFEM_NL_NEOHOOKE3D = 3,  /* "neohooke3d"  Example330:49-57 (DW); params mu, lambda */
     EXTFEM_NL_RCD = 4,         /* "rcd"         Example108:40-45                        */
     EXTFEM_NL_NLPOISSON105 = 5,/* "nlpoisson105" Example105:45-50 [exp(u)-exp(-u), eps grad u]; params eps */
-    EXTFEM_NL_STVENANT230 = 6  /* "stvenant230" Example230:39-72 (2D, [grad(u)]); params R, lambda[R], mu[R], epsT[R]
+    EXTFEM_NL_STVENANT230 = 6, /* "stvenant230" Example230:39-72 (2D, [grad(u)]); params R, lambda[R], mu[R], epsT[R]
                                                  indexed by the cell region                  */
+    EXTFEM_NL_POROUS106 = 7    /* "porous106"   Example106:47-52: test [grad(u)], args [id(u), grad(u)], m u^(m-1) grad u; params m */
 };
 enum { /* ItemIntegrator kernels (item_integrator.jl:26-28, 71-81 and the examples' exact_error! closures) */
     EXTFEM_II_STANDARD = 1,         /* "ii_standard"      result = input (ItemIntegrator(oa_args), item_integrator.jl:78-81) */

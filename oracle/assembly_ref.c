@@ -217,7 +217,8 @@ enum {
     ORA_NL_NEOHOOKE3D = 3, /* examples/Example330_HyperElasticity.jl:49-57 (DW) ; params mu,lambda */
     ORA_NL_RCD = 4,        /* examples/Example108_RobinBoundaryCondition.jl:40-45 (any dim: u*du/dx1+u ; grad) */
     ORA_NL_NLPOISSON105 = 5, /* examples/Example105_NonlinearPoissonEquation.jl:45-50 ; params eps */
-    ORA_NL_STVENANT230 = 6 /* examples/Example230_NonlinearElasticity.jl:39-72 ; params R, lambda[R], mu[R], epsT[R] */
+    ORA_NL_STVENANT230 = 6, /* examples/Example230_NonlinearElasticity.jl:39-72 ; params R, lambda[R], mu[R], epsT[R] */
+    ORA_NL_POROUS106 = 7   /* examples/Example106_NonlinearDiffusion.jl:47-52 ; params m */
 };
 enum {
     ORA_II_STANDARD = 1,   /* ExtendableFEMBase.standard_kernel (item_integrator.jl:78-81)              */
@@ -371,6 +372,11 @@ static int nl_kernel(int id, int dim, double complex *r, const double complex *i
     case ORA_NL_NLPOISSON105: { /* u, grad u ; result[1] = exp(u) - exp(-u) ; result[2] = eps * grad u */
         r[0] = cexp(in[0]) - cexp(-in[0]);
         for (int d = 0; d < dim; ++d) r[1 + d] = p[0] * in[1 + d];
+        return 0;
+    }
+    case ORA_NL_POROUS106: { /* input u, grad u ; result = m u^(m-1) grad u (dim components) */
+        double complex um1 = (p[0] == 2.0) ? in[0] : cpow(in[0], p[0] - 1.0);
+        for (int d = 0; d < dim; ++d) r[d] = p[0] * um1 * in[1 + d];
         return 0;
     }
     case ORA_NL_STVENANT230: { /* input = grad(u) as a vector, Voigt strain, isotropic stress, per-region material */

@@ -23,7 +23,7 @@ _lib = None
 OP_ID, OP_GRAD, OP_DIV, OP_SYMGRAD_VOIGT = 0, 1, 2, 3
 BLK = dict(standard=1, dcr=2, stokes=3, linnse7=4, hooke_grad=5, hooke_voigt=6, convect_args=7, robin108=8)
 LIN = dict(constant_one=1, constant_params=2, xy=3, sincos301=4, tabulated=5, exp2x=6, step105=7)
-NL = dict(nse2d=1, linnse7=2, neohooke3d=3, rcd=4, nlpoisson105=5, stvenant230=6)
+NL = dict(nse2d=1, linnse7=2, neohooke3d=3, rcd=4, nlpoisson105=5, stvenant230=6, porous106=7)
 II = dict(ii_standard=1, l2norm=2, l2diff_tabulated=3, l2err_sincos301=4, l2err_exp108=5)
 
 

@@ -6,6 +6,7 @@ import numpy as np
 
 GOLDEN = {
     "Example105": 0.4812118250102083,       # examples/Example105_NonlinearPoissonEquation.jl:80  maximum(sol.entries)
+    "Example106": 4.641588833612778,        # examples/Example106_NonlinearDiffusion.jl:132       maximum(sol.entries)
     "Example108": 9.062544216508815e-6,     # examples/Example108_RobinBoundaryCondition.jl:95    L2 error
     "Example201": 1.1140313632246377,       # examples/Example201_PoissonProblem.jl:80            sum(sol.entries)
     "Example205": 0.041490419236077006,     # examples/Example205_HeatEquation.jl:97              maximum(sol.entries)
@@ -177,3 +178,43 @@ def example205(pkg, make_backend, nrefs=2, T=1.0, tau=1e-3, order=2, moment_quad
         r[bd] = 0.0
         sol = sol + lu.solve(r)
     return float(sol.max()), sol, dict(K=K, M=M)
+
+
+def example106(pkg, make_backend, m=2.0, h=0.05, t0=0.001, T=0.01, order=1, tau=1e-4):
+    """Example106:57-135 (use_diffeq = false): porous medium equation u_t = (u^m)_xx in 1D, backward Euler with the lumped mass
+    matrix (lump = 2), ONE Newton step per time step (SolverConfiguration maxiterations = 1), NonlinearOperator whose test
+    operators [grad(u)] differ from its arguments [id(u), grad(u)].  As in the reference, the returned vector is OVERWRITTEN with
+    the interpolated Barenblatt solution at t = T before the test reads its maximum (Example106:118,132), so the golden pins
+    the interpolation; the FE solution of the time loop is returned beside it and must be close to that profile."""
+    import scipy.sparse.linalg as spla
+    pr = pkg.problem
+
+    def u_exact(x, t):
+        tx = t ** (-1.0 / (m + 1.0))
+        xx = (x * tx) ** 2
+        xx = np.maximum(1 - xx * (m - 1) / (2.0 * m * (m + 1)), 0.0)
+        return tx * xx ** (1.0 / (m - 1.0))
+
+    n = int(round(2 / h))
+    grid = pkg.simplexgrid(np.linspace(-1.0, 1.0, n + 1))
+    FES = [pkg.FESpace(pkg.H1Pk(1, 1, order), grid)]
+    be = make_backend(FES)
+    u = pr.Unknown("u")
+    blocks = {u: 0}
+    be.zero()
+    be.assemble(pr.BilinearOperator([pr.id(u)], lump=2), blocks, None)
+    M = be.system()[0]
+    nl = pr.NonlinearOperator("porous106", [pr.grad(u)], [pr.id(u), pr.grad(u)], params=[m], bonus_quadorder=2)
+    x = FES[0].dof_coordinates()[:, 0]
+    sol = u_exact(x, t0)
+    for _ in range(int(np.floor((T - t0) / tau))):
+        old = sol.copy()
+        be.zero()
+        be.assemble(nl, blocks, sol)
+        A, b = be.system()
+        A = (A + M / tau).tocsc()
+        b = b + M @ old / tau
+        sol = sol + spla.spsolve(A, b - A @ sol)
+    fe = sol
+    sol = u_exact(x, T)                       # interpolate!(sol[1], u_exact!; time = T) -- Example106:118
+    return float(sol.max()), sol, dict(fe=fe, x=x)

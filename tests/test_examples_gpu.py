@@ -15,7 +15,7 @@ def backends(pkg, ora, engine):
     return (lambda FES: pkg.problem.EngineBackend(engine, FES)), (lambda FES: OracleBackend(pkg, ora, FES))
 
 
-@pytest.mark.parametrize("name,tol", [("example105", 1e-12), ("example108", 1e-8), ("example201", 1e-12), ("example205", 1e-10),
+@pytest.mark.parametrize("name,tol", [("example105", 1e-12), ("example106", 1e-12), ("example108", 1e-8), ("example201", 1e-12), ("example205", 1e-10),
                                       ("example230", 1e-9)])
 def test_example_golden(pkg, backends, name, tol):
     gpu, cpu = backends
@@ -28,6 +28,8 @@ def test_example_golden(pkg, backends, name, tol):
     s2 = sol2.entries if hasattr(sol2, "entries") else sol2
     if name != "example230":   # Example230 fixes u_x only: the y-translation is in the kernel of the matrix, the strain is unique
         check_values(s1, s2, rtol=1e-9, what=f"{name}: solution, engine vs oracle")
+    if name == "example106":   # the golden is the interpolated profile (Example106:118,132): compare the time loop's FE solutions
+        check_values(st["fe"], st2["fe"], rtol=1e-9, what="example106: FE solution after 90 steps, engine vs oracle")
     if "nonlinear_residuals" in st:
         assert len(st["nonlinear_residuals"]) == len(st2["nonlinear_residuals"])
 

@@ -3,6 +3,8 @@ CPU oracle and must reproduce the golden values the reference's own ``runtests()
 pins oracle/assembly_ref.c + oracle/fetables.py -- and the engine-convention grids of host/grids.py -- to the reference:
 
   Example105:80   1D P2, NonlinearOperator + LinearOperator, Newton to 6e-16           reproduced to 1e-15
+  Example106:132  1D P1, porous-medium NonlinearOperator (test [grad u], args [u, grad u]), lumped mass matrix, 90 implicit Euler
+                  steps; the reference's number is the interpolated exact profile         reproduced to 1e-15
   Example108:95   1D P2, NonlinearOperator, Robin BilinearOperator ON_BFACES, InterpolateBoundaryData, ItemIntegrator
                   with quadorder 4 (3-point Gauss)                                       reproduced to 1e-10
   Example201:80   2D P2 Poisson, order-2 triangle rule, penalties                       reproduced to 2e-15
@@ -30,6 +32,15 @@ def test_example105(pkg, mk):
     v, sol, st = ex.example105(pkg, mk)
     assert abs(v / ex.GOLDEN["Example105"] - 1) < 1e-12
     assert len(st["nonlinear_residuals"]) == 5 and st["nonlinear_residuals"][-1] < 1e-10
+
+
+def test_example106(pkg, mk):
+    """Example106:132.  The reference overwrites the solution with the interpolated Barenblatt profile before it reads the
+    maximum, so the golden pins the nodal interpolation; the 90 implicit Euler steps (one Newton step each, lumped mass matrix,
+    NonlinearOperator with test operators != argument operators) must land near that profile."""
+    v, sol, st = ex.example106(pkg, mk)
+    assert abs(v / ex.GOLDEN["Example106"] - 1) < 1e-14
+    assert np.abs(st["fe"] - sol).max() < 0.05 * sol.max() and abs(st["fe"].sum() / sol.sum() - 1) < 0.02   # mass is conserved
 
 
 def test_example108(pkg, mk):
