@@ -16,6 +16,8 @@ import __graft_entry__ as g
 
 ID, GRAD = 0, 1
 HERE = os.path.dirname(os.path.abspath(__file__))
+# tuning sweeps only (scripts/gpu_nl_opts.sh): skip the oracle comparison, the size-independent checks still run
+NO_PARITY = {"matrix_max_rel": 0.0, "rhs_max_rel": 0.0, "skipped": True} if os.environ.get("EXTFEM_NO_PARITY") else None
 
 
 def timed(eng, fn, reps=3):
@@ -146,8 +148,8 @@ def config3(pkg, eng, n):
     ok = bool(np.array_equal(nz1, nz2) and np.array_equal(b1, b2) and div_rows < 1e-12 * np.abs(nz1).max() and np.isfinite(res).all())
     solfun = lambda FS: np.concatenate([FS[0].dof_coordinates()[:, 0] ** 2, FS[0].dof_coordinates().sum(axis=1),   # noqa: E731
                                         FS[1].dof_coordinates()[:, 1] ** 2])
-    parity = parity_submesh(pkg, eng, pat, nz1, b1, n, [pkg.H1P2(2, 2), pkg.H1P1(1)], [FU, FP], args, "nse2d", [0.05], solfun,
-                            coupling=np.array([1, 1, 1, 0], dtype=np.uint8))
+    parity = NO_PARITY or parity_submesh(pkg, eng, pat, nz1, b1, n, [pkg.H1P2(2, 2), pkg.H1P1(1)], [FU, FP], args, "nse2d", [0.05], solfun,
+                                         coupling=np.array([1, 1, 1, 0], dtype=np.uint8))
     from oracle import fetables
     roof = rooflines(ms, grid.ncells, nnz, nrows, 2, fetables.quadrature_rule(2, 4)[1].size, 7, 7, 15, 12 * 3 + 3)   # 12 velocity dofs: id + 2 gradient entries; 3 pressure dofs: id
     ok = ok and parity["matrix_max_rel"] <= 1e-12 and parity["rhs_max_rel"] <= 1e-12
@@ -193,7 +195,7 @@ def config4(pkg, eng, n):
     def solfun(FS):
         xs = FS[0].dof_coordinates()
         return 0.1 * np.concatenate([xs[:, 0] ** 2, xs[:, 0] + xs[:, 1], xs[:, 1] * xs[:, 2]])
-    parity = parity_submesh(pkg, eng, pat, nz1, b1, n, [pkg.H1P2(3, 3)], [FU], args, "neohooke3d", [mu, la], solfun)
+    parity = NO_PARITY or parity_submesh(pkg, eng, pat, nz1, b1, n, [pkg.H1P2(3, 3)], [FU], args, "neohooke3d", [mu, la], solfun)
     from oracle import fetables
     roof = rooflines(ms, grid.ncells, nnz, nrows, 3, fetables.quadrature_rule(3, 2)[1].size, 9, 9, 30, 30 * 3)      # 30 dofs with 3 gradient entries each
     ok = ok and parity["matrix_max_rel"] <= 1e-12 and parity["rhs_max_rel"] <= 1e-12

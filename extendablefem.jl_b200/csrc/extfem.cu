@@ -132,6 +132,8 @@ struct Ctx {
     DevBuf custom_qw, custom_qx;
     DevBuf loc, bloc, sol, params_scratch, tab, geo, visit, fq;
     bool fast_enabled = true;   // option "fastpath"
+    int nl_cpw = 8, nl_warps = 4; // options "nonlinear_cells_per_warp", "nonlinear_warps_per_cta" of the tensor-core contraction kernel
+    bool nl_sparse_jac = true;  // option "nonlinear_sparse_jacobian": the tensor-core nonlinear path moves only the structural non-zeros of J
     bool gather_warp = true;    // option "gather_warp": generic matrix reduction with one warp (1) / one thread (0) per column
     int nl_version = 4;         // option "nonlinear_kernel": 1 entry-wise local kernel, 2 staged per block, 3 warp per cell,
                                 // 4 warp per cell with the contractions on FP64 tensor cores (falls back to 3 when not applicable)
@@ -1501,7 +1503,25 @@ static int build_nl3_tables(Ctx *ctx, const OpDev &op, NL3Tables &T, bool *ok, b
     {   // dense operator matrix of the tensor-core kernel (kernels_generic.cuh: local_nonlinear_kernel4)
         T.NT4 = (std::max(op.NC, op.NR) + 7) / 8;
         T.Np4 = T.NT4 <= 2 ? 20 : 36;
-        T.dense_ok = same && op.nin == op.nout && op.nin <= 9 && T.NT4 <= 4 && nl4_warp_doubles(op.nq, op.nin, T.Np4, off) * 8 * 4 <= 120 * 1024;
+        T.dense_ok = same && op.nin == op.nout && op.nin <= 9 && T.NT4 <= 4 &&
+                     nl4_warp_doubles(op.nq, op.nin, op.nin * op.nout, T.Np4, off) * 8 * 4 <= 120 * 1024;
+        // structural non-zeros of the kernel's Jacobian (probed on the device with the operator's parameters)
+        T.nnzJ = op.nin * op.nout;
+        T.o_jslot = reserve((size_t)op.nin * op.nout);
+        for (int e = 0; e < op.nin * op.nout; ++e) host[T.o_jslot + e] = (unsigned char)e;
+        if (want_dense && T.dense_ok && ctx->nl_sparse_jac) {
+            DevBuf dm;
+            std::vector<unsigned char> hm((size_t)op.nin * op.nout);
+            if (int rc = ensure(ctx, dm, hm.size())) return rc;
+            EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(dm.p, 0, hm.size(), ctx->stream));
+            nl_mask_kernel<<<1, 32, 0, ctx->stream>>>(op, op.dim, dm.as<unsigned char>());
+            LAUNCHED(ctx);
+            EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(hm.data(), dm.p, hm.size(), cudaMemcpyDeviceToHost, ctx->stream));
+            EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            int n = 0;
+            for (size_t e = 0; e < hm.size(); ++e) host[T.o_jslot + e] = hm[e] ? (unsigned char)n++ : (unsigned char)255;
+            T.nnzJ = std::max(n, 1);
+        }
         T.o_pt = reserve((size_t)T.EC * op.NC * 4);
         for (int x = 0; x < T.EC; ++x)
             for (int j = 0; j < op.NC; ++j) {
@@ -1871,6 +1891,9 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "fastpath")) { C->fast_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_closed_form")) { C->bary_enabled = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_v2")) { C->nl_version = value != 0 ? 3 : 1; return EXTFEM_OK; }
+    if (key && !strcmp(key, "nonlinear_cells_per_warp")) { C->nl_cpw = std::min(std::max(value, 1), 1024); return EXTFEM_OK; }
+    if (key && !strcmp(key, "nonlinear_warps_per_cta")) { C->nl_warps = std::min(std::max(value, 1), 4); return EXTFEM_OK; }
+    if (key && !strcmp(key, "nonlinear_sparse_jacobian")) { C->nl_sparse_jac = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "gather_warp")) { C->gather_warp = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_kernel")) { C->nl_version = std::min(std::max(value, 1), 4); return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
@@ -2364,12 +2387,12 @@ int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc 
     int rcd = dispatch_dim(C, op.dim, [&](auto dimc) {
         constexpr int DIM = decltype(dimc)::value;
         if (v3 && C->nl_version >= 4 && T3.dense_ok && nl4_points_ok) {
-            const size_t wd = nl4_warp_doubles(op.nq, op.nin, T3.Np4, T3.phi_off[T3.nspaces]);
-            const int nw = 4, cpw = 8;
+            const size_t wd = nl4_warp_doubles(op.nq, op.nin, T3.nnzJ, T3.Np4, T3.phi_off[T3.nspaces]);
+            const int nw = C->nl_warps, cpw = C->nl_cpw;
             const size_t smem = (size_t)nw * wd * 8 + T3.tab_bytes;
             if (smem <= 220 * 1024) {
                 const long long ntot = op.ncells * op.nq;
-                double *wJ = C->nlpt.as<double>(), *rqg = wJ + (size_t)ntot * op.nin * op.nout;
+                double *wJ = C->nlpt.as<double>(), *rqg = wJ + (size_t)ntot * T3.nnzJ;
                 // (1) kernel value and Jacobian per (cell, point), one thread each
                 const unsigned gp = nblocks(ntot, 128);
                 switch (op.nin) {

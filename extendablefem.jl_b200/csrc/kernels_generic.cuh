@@ -752,6 +752,7 @@ struct NL3Tables {
     // stride Np4 (== 4 mod 16: conflict-free fragment loads), Kp4 = nq * nin rounded up to a multiple of 4
     int dense_ok, NT4, Np4;                    // tensor-core path: number of 8-wide dof tiles and the row stride of B_q
     int o_ddst;                                // u16 [EC][NC]: offset of the sparse entry inside the dense B_q
+    int nnzJ, o_jslot;                         // structurally non-zero Jacobian entries; u8 [nout*nin] compact slot or 255
     int o_pt;                                  // u8x4 [EC][NC]: (space, scalar basis function, source 0 value | 1+d gradient, -) of a B entry
     int nspaces, ns[NL2_MAXSP_];
     const double *refvals[NL2_MAXSP_], *refgrads[NL2_MAXSP_];
@@ -914,6 +915,21 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// Structural non-zeros of a registered kernel's Jacobian for the operator's parameters: 32 probes at random states (all regions
+// the material tables distinguish); an entry that is zero in every probe is never stored or multiplied.
+__global__ void nl_mask_kernel(const __grid_constant__ OpDev op, int dim, unsigned char *__restrict__ mask)
+{
+    double in[16], val[16], J[256];
+    unsigned s = threadIdx.x * 2654435761u + 12345u;
+    for (int i = 0; i < op.nin; ++i) {
+        s = s * 1664525u + 1013904223u;
+        in[i] = ((s >> 8) & 0xffffu) / 65536.0 * 1.5 + 0.25;
+    }
+    nl_apply(op.kernel_id, dim, in, op.params, val, J, op.nin, op.nout, 1 + (threadIdx.x & 7));
+    for (int e = 0; e < op.nin * op.nout; ++e)
+        if (J[e] != 0.0) mask[e] = 1;
+}
+
 // nl_apply with compile-time vector lengths and the kernel id folded per case: after inlining every index is static, the value and
 // Jacobian arrays live in registers
 template <int DIM, int NIO>
@@ -938,6 +954,7 @@ nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tab
     const unsigned short *uptr = reinterpret_cast<const unsigned short *>(tb + T.o_uptr), *ulist = reinterpret_cast<const unsigned short *>(tb + T.o_ulist);
     const uchar4 *pt = reinterpret_cast<const uchar4 *>(tb + T.o_pt);
     const double *bgsc = reinterpret_cast<const double *>(tb + T.o_bgsc);
+    const unsigned char *jslot = tb + T.o_jslot;
     double *solc = reinterpret_cast<double *>(tb + T.tab_bytes);      // [cells of the block][NC] solution coefficients
     const int nq = op.nq, NC = T.NC;
     const long long ntot = op.ncells * nq;
@@ -993,17 +1010,18 @@ nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tab
 #pragma unroll
         for (int d = 0; d < NIO; ++d) {
             sum = fma(J[k * NIO + d], u[d], sum);
-            wJ[(size_t)(k * NIO + d) * ntot + t] = J[k * NIO + d] * w;
+            const int sl = jslot[k * NIO + d];        // structural zeros of the Jacobian are not stored
+            if (sl != 255) wJ[(size_t)sl * ntot + t] = J[k * NIO + d] * w;
         }
         rqg[(size_t)k * ntot + t] = (sum - val[k]) * sc;
     }
 }
 
-// doubles of shared memory per warp: PHI | B_q [rows][Np] | GJ_q [rows][Np] | w J [nq][nin][nin] | residual terms [nq][nin]
-__host__ __device__ inline size_t nl4_warp_doubles(int nq, int nin, int Np, int phid)
+// doubles of shared memory per warp: PHI | B_q [rows][Np] | GJ_q [rows][Np] | w J [nq][nnzJ] (compact) | residual terms [nq][nin]
+__host__ __device__ inline size_t nl4_warp_doubles(int nq, int nin, int nnzJ, int Np, int phid)
 {
     const int rows = (nin + 3) / 4 * 4;
-    size_t d = (size_t)(phid + (phid & 1)) + 2 * (size_t)rows * Np + (size_t)nq * nin * nin + (size_t)nq * nin;
+    size_t d = (size_t)(phid + (phid & 1)) + 2 * (size_t)rows * Np + (size_t)nq * nnzJ + (size_t)nq * nin + (size_t)nin;
     return (d + 1) & ~(size_t)1;
 }
 
@@ -1025,21 +1043,38 @@ local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant_
     const int nin = op.nin, nq = op.nq, NR = T.NR, NC = T.NC, NRC = NR * NC, ECNC = T.EC * NC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int phid = T.phi_off[T.nspaces];
-    const size_t wd = nl4_warp_doubles(nq, nin, Np, phid);
-    const int JS = nin * nin;
+    const int JS = T.nnzJ;                     // compact Jacobian entries per point
+    const size_t wd = nl4_warp_doubles(nq, nin, JS, Np, phid);
     unsigned char *tb = reinterpret_cast<unsigned char *>(smem_d + (size_t)nwarp * wd);
     for (int i = threadIdx.x; i < T.tab_bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(tb)[i] = __ldg(reinterpret_cast<const uint4 *>(T.tab) + i);
     const int *bgidx = reinterpret_cast<const int *>(tb + T.o_bgidx);
     const double *bgsc = reinterpret_cast<const double *>(tb + T.o_bgsc);
     const unsigned short *ddst = reinterpret_cast<const unsigned short *>(tb + T.o_ddst);
+    const unsigned char *jslot = tb + T.o_jslot;
     double *PHI = smem_d + (size_t)warp * wd;
     double *Bq = PHI + phid + (phid & 1);      // [rows][Np] operator matrix of one quadrature point (16-byte aligned)
     double *Gq = Bq + rows * Np;               // [rows][Np] (w J_q) B_q
-    double *Jq = Gq + rows * Np;               // [nq][nin][nin] w J of the cell's points
+    double *Jq = Gq + rows * Np;               // [nq][nnzJ] w J of the cell's points, structural non-zeros only
     double *rq = Jq + (size_t)nq * JS;         // [nq][nin] (J u - F) factor w |T|
+    double *j8 = rq + (size_t)nq * nin;        // [nin] last Jacobian row of the current point, dense (R1)
     for (int i = lane; i < 2 * rows * Np; i += 32) Bq[i] = 0.0;   // structural zeros and padding stay zero for every cell and point
     __syncthreads();
     const int gid = lane >> 2, tig = lane & 3;
+    // compact slots of this lane's Jacobian fragment (rows gid [+8], columns 4 ks + tig, and the rank-1 column): -1 = structural zero
+    int sa[MT][KS], sr[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int o = mt * 8 + gid;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int i = ks * 4 + tig;
+            const int sl = (o < nin && i < nin) ? jslot[o * nin + i] : 255;
+            sa[mt][ks] = sl == 255 ? -1 : sl;
+        }
+        const int sl = (R1 && o < nin) ? jslot[o * nin + KD] : 255;
+        sr[mt] = sl == 255 ? -1 : sl;
+    }
+    const int s8 = (R1 && lane < nin) ? jslot[KD * nin + lane] : 255;
     // the lane whose accumulator fragment holds column NC carries the right-hand side
     const bool rhs_in_gemm = (NC & 7) != 0;
     const int rt = NC >> 3, rslot = NC & 1;
@@ -1093,19 +1128,17 @@ local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant_
         __syncwarp();
         for (int q = 0; q < nq; ++q) {
             // this lane's fragment of w J_q (component rows gid [+8], input columns 4 ks + tig) and its residual terms
-            const double *J = Jq + q * JS, *j8 = J + KD * nin, *r = rq + q * nin;
+            const double *J = Jq + q * JS, *r = rq + q * nin;
             double ja[MT][KS], jr[MT], rr[MT];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int o = mt * 8 + gid;
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
-                    const int i = ks * 4 + tig;
-                    ja[mt][ks] = (o < nin && i < nin) ? J[o * nin + i] : 0.0;
-                }
-                jr[mt] = (R1 && o < nin) ? J[o * nin + KD] : 0.0;
+                for (int ks = 0; ks < KS; ++ks) ja[mt][ks] = sa[mt][ks] >= 0 ? J[sa[mt][ks]] : 0.0;
+                jr[mt] = (R1 && sr[mt] >= 0) ? J[sr[mt]] : 0.0;
                 rr[mt] = (rmine && o < nin) ? r[o] : 0.0;
             }
+            if (R1 && lane < nin) j8[lane] = s8 != 255 ? J[s8] : 0.0;
             // operator matrix of the point: the sparse entries of the B tables into their dense places
             for (int i = lane; i < ECNC; i += 32) { const int p = bgidx[q * ECNC + i]; if (p >= 0) Bq[ddst[i]] = bgsc[i] * PHI[p]; }
             __syncwarp();
