@@ -14,7 +14,7 @@ namespace extfem {
 
 constexpr int MAXBLOCKS = 8;
 constexpr int GATHER_THREADS = 128;
-constexpr int GATHER_MAXNNZ = 6144; // doubles of shared memory per CTA (48 KB)
+constexpr int GATHER_MAXNNZ = 6112; // doubles of a column chunk in shared memory (48 KB per CTA with the 32 dummy targets of the warp kernel)
 
 template <typename PosT>
 struct GatherArgs {
@@ -104,7 +104,7 @@ template <typename PosT, bool TR, int H>
 __global__ void __launch_bounds__(GATHER_WARP_THREADS, 3)
 gather_columns_warp_kernel(const __grid_constant__ GatherArgs<PosT> g)
 {
-    __shared__ double acc[GATHER_MAXNNZ];
+    __shared__ double acc[GATHER_MAXNNZ + 32];   // + one dummy target per lane
     const int k0 = g.chunkptr[blockIdx.x], k1 = g.chunkptr[blockIdx.x + 1];
     const long long base = g.colptr[k0];
     const int n = (int)(g.colptr[k1] - base);
@@ -135,53 +135,54 @@ gather_columns_warp_kernel(const __grid_constant__ GatherArgs<PosT> g)
     // this warp's run of columns (the chunk has at most GATHER_THREADS = 32 nw columns)
     const int cpw = (k1 - k0 + nw - 1) / nw;
     const int ka = min(k0 + warp * cpw, k1), kb = min(ka + cpw, k1);
-    const long long pend = lane < kb - ka ? adjptr[ka + lane + 1] : 0x7fffffffffffffffLL;
+    // pair indices relative to the start of the run: 32-bit arithmetic in the loop, clamped loads instead of branches, and a
+    // per-lane dummy accumulator for lanes without a target, so that the loop body is straight-line code
+    const long long P0 = adjptr[ka];
+    const int nrun = (int)(adjptr[kb] - P0);
+    const int pend = lane < kb - ka ? (int)(adjptr[ka + lane + 1] - P0) : 0x7fffffff;
     const int cbase = lane < kb - ka ? (int)(g.colptr[ka + lane] - base) : 0;
-    const long long P0 = adjptr[ka], P1 = adjptr[kb];
-    for (int t0 = 0; t0 < g.nrows_g; t0 += W) {
+    const int *adjc = adjcell + P0;
+    const unsigned char *adjl = adjloc + P0;
+    const int NRpat = g.NRpat, dummy = GATHER_MAXNNZ + lane;
+    for (int t0 = 0; t0 < g.nrows_g && nrun > 0; t0 += W) {
         const bool on = t0 + tl < g.nrows_g;
         const int rm = on ? g.rowmap[t0 + tl] : 0;
         const double *lsrc = g.loc + (on ? g.rowsrc[t0 + tl] : 0) * rstride + cloc * cstride;
-        const PosT *pm = posmap + rm;
+        const PosT *pm = posmap + P0 * NRpat + rm;
         // (cell, local column) of the pairs one batch ahead of the value loads
         int ncell[U], nkl[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long pp = P0 + u * H + sub;
-            ncell[u] = pp < P1 ? adjcell[pp] : 0;
-            nkl[u] = pp < P1 ? adjloc[pp] : 0;
+            const int pp = min(u * H + sub, nrun - 1);
+            ncell[u] = adjc[pp]; nkl[u] = adjl[pp];
         }
-        for (long long p = P0; p < P1; p += U * H) {
-            int ab[U];
-            PosT pos[U];
+        for (int p = 0; p < nrun; p += U * H) {
+            int ad[U];
             double v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const long long pp = p + u * H + sub;
-                pos[u] = SENT; v[u] = 0.0; ab[u] = 0;
+                const int pu = p + u * H, pp = pu + sub;
                 // column of the pair = number of columns of the run that end at or before it
-                int col = __popc(__ballot_sync(0xffffffffu, pend <= p + u * H));
-                if (H == 2) { const int col1 = __popc(__ballot_sync(0xffffffffu, pend <= p + u * H + 1)); col = sub ? col1 : col; }
-                ab[u] = __shfl_sync(0xffffffffu, cbase, min(col, 31));
-                if (pp < P1 && on) {
-                    pos[u] = pm[pp * g.NRpat];
-                    v[u] = lsrc[(long long)ncell[u] * CS + nkl[u] * cstride];
-                }
+                int col = __popc(__ballot_sync(0xffffffffu, pend <= pu));
+                if (H == 2) { const int col1 = __popc(__ballot_sync(0xffffffffu, pend <= pu + 1)); col = sub ? col1 : col; }
+                const int ab = __shfl_sync(0xffffffffu, cbase, min(col, 31));
+                const PosT pos = pm[(long long)(min(pp, nrun - 1) * NRpat)];
+                v[u] = lsrc[(long long)ncell[u] * CS + nkl[u] * cstride];
+                ad[u] = (on && pp < nrun && pos != SENT) ? ab + (int)pos : dummy;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const long long pp = p + U * H + u * H + sub;
-                ncell[u] = pp < P1 ? adjcell[pp] : 0;
-                nkl[u] = pp < P1 ? adjloc[pp] : 0;
+                const int pp = min(p + (U + u) * H + sub, nrun - 1);
+                ncell[u] = adjc[pp]; nkl[u] = adjl[pp];
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const double w = TR ? scale * v[u] : v[u];
                 if (H == 2) {
-                    if (sub == 0 && pos[u] != SENT) acc[ab[u] + pos[u]] += w;
+                    if (sub == 0) acc[ad[u]] += w;
                     __syncwarp();
-                    if (sub == 1 && pos[u] != SENT) acc[ab[u] + pos[u]] += w;
-                } else if (pos[u] != SENT) acc[ab[u] + pos[u]] += w;
+                    if (sub == 1) acc[ad[u]] += w;
+                } else acc[ad[u]] += w;
                 __syncwarp();              // another lane may own the same row in the next cell
             }
         }
