@@ -1503,7 +1503,7 @@ static int build_nl3_tables(Ctx *ctx, const OpDev &op, NL3Tables &T, bool *ok, b
     {   // dense operator matrix of the tensor-core kernel (kernels_generic.cuh: local_nonlinear_kernel4)
         T.NT4 = (std::max(op.NC, op.NR) + 7) / 8;
         T.Np4 = T.NT4 <= 2 ? 20 : 36;
-        T.dense_ok = same && op.nin == op.nout && op.nin <= 9 && T.NT4 <= 4 &&
+        T.dense_ok = same && op.nin == op.nout && op.nin <= 9 && T.NT4 <= 4 && T.EC * op.NC <= 128 &&
                      nl4_warp_doubles(op.nq, op.nin, op.nin * op.nout, T.Np4, off) * 8 * 4 <= 120 * 1024;
         // structural non-zeros of the kernel's Jacobian (probed on the device with the operator's parameters)
         T.nnzJ = op.nin * op.nout;

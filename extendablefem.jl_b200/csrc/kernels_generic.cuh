@@ -1075,6 +1075,22 @@ local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant_
         sr[mt] = sl == 255 ? -1 : sl;
     }
     const int s8 = (R1 && lane < nin) ? jslot[KD * nin + lane] : 255;
+    // this lane's entries of the operator matrix (at most 4 x 32 sparse entries: NC <= 32 dofs with <= 4 operator entries each):
+    // dense place, scale and the PHI index as a linear function of the point -- nothing of it depends on the cell
+    // (kept in registers when the accumulator tiles leave room: NT <= 3; the 16 tiles of NT = 4 need them all)
+    constexpr bool HOIST = NT <= 3;
+    constexpr int NIT = HOIST ? 4 : 1;
+    int sdst[NIT], sp0[NIT], sdp[NIT];
+    double ssc[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT && HOIST; ++it) {
+        const int i = it * 32 + lane;
+        const bool live = i < ECNC && bgidx[i] >= 0;
+        sdst[it] = live ? ddst[i] : -1;
+        sp0[it] = live ? bgidx[i] : 0;
+        sdp[it] = (live && nq > 1) ? bgidx[ECNC + i] - bgidx[i] : 0;
+        ssc[it] = live ? bgsc[i] : 0.0;
+    }
     // the lane whose accumulator fragment holds column NC carries the right-hand side
     const bool rhs_in_gemm = (NC & 7) != 0;
     const int rt = NC >> 3, rslot = NC & 1;
@@ -1140,7 +1156,13 @@ local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant_
             }
             if (R1 && lane < nin) j8[lane] = s8 != 255 ? J[s8] : 0.0;
             // operator matrix of the point: the sparse entries of the B tables into their dense places
-            for (int i = lane; i < ECNC; i += 32) { const int p = bgidx[q * ECNC + i]; if (p >= 0) Bq[ddst[i]] = bgsc[i] * PHI[p]; }
+            if (HOIST) {
+#pragma unroll
+                for (int it = 0; it < NIT; ++it)
+                    if (sdst[it] >= 0) Bq[sdst[it]] = ssc[it] * PHI[sp0[it] + q * sdp[it]];
+            } else {
+                for (int i = lane; i < ECNC; i += 32) { const int p = bgidx[q * ECNC + i]; if (p >= 0) Bq[ddst[i]] = bgsc[i] * PHI[p]; }
+            }
             __syncwarp();
             // GJ_q = (w J_q) B_q: tiles of 8 components x 8 dofs, k-steps of 4 input components
 #pragma unroll
