@@ -123,10 +123,11 @@ def parity_vs_oracle(pkg, eng, pat, n, nzl, keys_engine, colptr, planes):
     them).  Returns max |engine - oracle| / max |oracle| over the compared entries."""
     from oracle import oracle as ora
     ora.build()
-    nzval, _ = eng.values_get(pat, want_b=False)
+    nzval, bvec = eng.values_get(pat)
     order = np.argsort(keys_engine)
     skeys = keys_engine[order]
     worst, count, ref_max = 0.0, 0, 0.0
+    worst_b, ref_b_max, count_b = 0.0, 0.0, 0
     h = 1.0 / n
     X = np.linspace(0.0, 1.0, n + 1)
     for k in planes:
@@ -138,10 +139,15 @@ def parity_vs_oracle(pkg, eng, pat, n, nzl, keys_engine, colptr, planes):
         gr = ora.OraArg(F.celldofs, 1, 2, ora.OP_GRAD)
         cp, rv = ora.structural_pattern([gr], [gr], (F.ndofs, F.ndofs))
         ref = ora.assemble_bilinear(om, [gr], [gr], "standard", csc=(cp, rv))
+        bref = np.zeros(F.ndofs)
+        ora.assemble_linear(om, [ora.OraArg(F.celldofs, 1, 2, ora.OP_ID)], bref, "sincos301", params=[1.0])
         w = 2 * n + 1
         cols = np.nonzero(keys // (w * w) == 2 * k)[0]                  # dofs on the plane z = k h
         gcol = order[np.searchsorted(skeys, keys[cols])]
         assert np.array_equal(keys_engine[gcol], keys[cols])
+        worst_b = max(worst_b, float(np.abs(bvec[gcol] - bref[cols]).max()))
+        ref_b_max = max(ref_b_max, float(np.abs(bref[cols]).max()))
+        count_b += cols.size
         for c, gc in zip(cols, gcol):
             a = ref[cp[c] - 1:cp[c + 1] - 1]
             b = nzval[colptr[gc] - 1:colptr[gc + 1] - 1]
@@ -149,7 +155,8 @@ def parity_vs_oracle(pkg, eng, pat, n, nzl, keys_engine, colptr, planes):
             worst = max(worst, float(np.abs(a - b).max()))
             ref_max = max(ref_max, float(np.abs(a).max()))
             count += a.size
-    return {"max_rel": worst / ref_max, "entries_checked": int(count), "planes_z_index": [int(k) for k in planes],
+    return {"max_rel": worst / ref_max, "entries_checked": int(count), "rhs_max_rel": worst_b / ref_b_max, "rhs_entries_checked": int(count_b),
+            "planes_z_index": [int(k) for k in planes],
             "against": "CPU oracle (oracle/assembly_ref.c) on the cube layers around each plane"}
 
 

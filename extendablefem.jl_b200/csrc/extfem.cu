@@ -154,6 +154,9 @@ struct Ctx {
     bool tmpl_permute_mesh = true; // option "template_permute_mesh": cell kernels read mesh copies in the transposed order
     int tmpl_mincols = 24;      // option "template_min_cols": smallest group of columns that gets a template
     int tmpl_classmask = 3;     // option "template_class_mask": tuning aid (time the short- / long-column warps alone)
+    int tmpl_flat = 0;          // option "template_flat_writeout": the walk kernel writes columns of up to this many entries out over
+                                // the flat (column, position) index (0: none)
+    bool rhs_local = true;      // option "rhs_local": fast right-hand side through cell-local vectors (one value per (dof, cell) pair)
     bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator
     long long launches = 0;
     cudaStream_t stream2 = nullptr;   // exchange stream: the interface reduction of the matrix runs beside the rhs assembly
@@ -1133,7 +1136,7 @@ static int launch_template(Ctx *ctx, Pattern &P, TemplatePlan &T, int b, int acc
     TPArgs A;
     A.wdesc = T.wdesc.as<int4>(); A.slotpb = T.slotpb.as<int>(); A.slotptr = T.slotptr.as<double *>();
     A.tmpl = T.tmpl.as<unsigned>(); A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
-    A.nwarps = T.nctas * TP_MAXW; A.ahead = ctx->tmpl_ahead * TP_MAXW; A.classmask = ctx->tmpl_classmask;
+    A.nwarps = T.nctas * TP_MAXW; A.ahead = ctx->tmpl_ahead * TP_MAXW; A.classmask = ctx->tmpl_classmask; A.flat = 0;
     (void)P; (void)b;
     auto k = tp_gather_kernel<EV, FIRST, CT>;
     if (int rc = smem_attr(ctx, (const void *)k, 227 * 1024)) return rc;
@@ -1201,7 +1204,7 @@ static int launch_fast_layout(Ctx *ctx, Pattern &P, FastPlan &F, TemplatePlan &T
         TPArgs A;
         A.wdesc = T.wdesc.as<int4>(); A.slotpb = T.slotpb.as<int>(); A.slotptr = T.slotptr.as<double *>();
         A.tmpl = T.walk.as<unsigned>(); A.geo = ctx->geo.as<double>(); A.Npad = T.Lg.Npad; A.overwrite = !accumulate;
-        A.nwarps = T.nctas * TP_MAXW; A.ahead = ctx->tmpl_ahead * TP_MAXW; A.classmask = ctx->tmpl_classmask;
+        A.nwarps = T.nctas * TP_MAXW; A.ahead = ctx->tmpl_ahead * TP_MAXW; A.classmask = ctx->tmpl_classmask; A.flat = ctx->tmpl_flat;
         if (ctx->tmpl_persistent && ctx->tmpl_classmask == 3 && T.walk_nlive[0] + T.walk_nlive[1] > 0) {
             // persistent CTAs: tmpl_persistent CTAs per SM (limited by the accumulator areas), the warps take groups from two queues
             auto k = first ? tw_gather_persistent_kernel<true> : tw_gather_persistent_kernel<false>;
@@ -1603,6 +1606,14 @@ static int build_nl3_tables(Ctx *ctx, const OpDev &op, NL3Tables &T, bool *ok, b
     return 0;
 }
 
+// rules (sizes of the engine's own rules up to order 4 or 5) the cell-local form of the fast right-hand side is compiled for
+static bool rhs_local_rule(int dim, int nq)
+{
+    if (dim == 1) return nq >= 1 && nq <= 4;
+    if (dim == 2) return nq == 1 || nq == 3 || nq == 4 || nq == 9;
+    return nq == 1 || nq == 4 || nq == 8;
+}
+
 // fast right-hand side: LinearOperator(f, [id(u)]) on a scalar P1/P2 space (linear_operator.jl:584-640).  Per cell the
 // point values factor*w_q*|T|*f(x_q) (structure-of-arrays, geometry order), per dof an owner-computes sum over the
 // adjacent cells driven by the template plan of the block.
@@ -1628,7 +1639,9 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
         for (int kl = 0; kl < ns; ++kl) phi[(size_t)kl * TP_NQMAX + q] = v[(size_t)q * ns + kl];
     if (int rca = const_acquire(ctx)) return rca;
     EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_phi, phi.data(), phi.size() * 8, 0, cudaMemcpyHostToDevice, ctx->stream));
-    if (int rc = ensure(ctx, ctx->fq, (size_t)T.Lg.Npad * op.nq * 8)) return rc;
+    // cell-local form (one plane per local dof) for the rules with a compile-time kernel, else point values (one plane per point)
+    const bool local = ctx->rhs_local && rhs_local_rule(dim, op.nq);
+    if (int rc = ensure(ctx, ctx->fq, (size_t)T.Lg.Npad * (local ? ns : op.nq) * 8)) return rc;
     double *bblk = P.b.as<double>() + P.rowoff[b];
     if (!accumulate && P.rowspaces.size() > 1) {
         for (size_t r = 0; r < P.rowspaces.size(); ++r) {
@@ -1648,7 +1661,28 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
     for (int i = 0; i < op.nparams; ++i) C.params[i] = op.params[i];
     C.factor = op.factor; C.Lg = T.Lg; C.fq = ctx->fq.as<double>();
     const unsigned gcell = nblocks(perm ? T.Lg.Npad : M.ncells, 256);
-    if (dim == 1) tp_rhs_cell_kernel<1><<<gcell, 256, 0, ctx->stream>>>(C);
+    if (local) {
+        RhsCellLocalArgs CL;
+        memset(&CL, 0, sizeof(CL));
+        CL.C = C; CL.ns = ns;
+        for (int q = 0; q < op.nq; ++q) {
+            CL.qw[q] = Q.w[q];
+            for (int r = 0; r < dim; ++r) CL.qx[q * dim + r] = Q.x[(size_t)q * dim + r];
+        }
+        bool launched = false;
+#define RHS_LOCAL(D, N) \
+        if (!launched && dim == D && op.nq == N) { \
+            if (op.kernel_id == EXTFEM_LIN_SINCOS301) tp_rhs_cell_local_kernel<D, N, EXTFEM_LIN_SINCOS301><<<gcell, 256, 0, ctx->stream>>>(CL); \
+            else tp_rhs_cell_local_kernel<D, N, -1><<<gcell, 256, 0, ctx->stream>>>(CL); \
+            launched = true; \
+        }
+        RHS_LOCAL(1, 1) RHS_LOCAL(1, 2) RHS_LOCAL(1, 3) RHS_LOCAL(1, 4)
+        RHS_LOCAL(2, 1) RHS_LOCAL(2, 3) RHS_LOCAL(2, 4) RHS_LOCAL(2, 9)
+        RHS_LOCAL(3, 1) RHS_LOCAL(3, 4) RHS_LOCAL(3, 8)
+#undef RHS_LOCAL
+        if (!launched) return fail(ctx, EXTFEM_ERR_CAPACITY, "fast right-hand side: no cell kernel for this rule");
+    }
+    else if (dim == 1) tp_rhs_cell_kernel<1><<<gcell, 256, 0, ctx->stream>>>(C);
     else if (dim == 2) tp_rhs_cell_kernel<2><<<gcell, 256, 0, ctx->stream>>>(C);
     else tp_rhs_cell_kernel<3><<<gcell, 256, 0, ctx->stream>>>(C);
     LAUNCHED(ctx);
@@ -1658,7 +1692,8 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
         A.nwarps = T.nctas * TP_MAXW; A.wdesc = T.wdesc.as<int4>(); A.slotcol = T.slotcol.as<int>(); A.slotpb = T.slotpb.as<int>();
         A.tmpl = T.tmpl.as<unsigned>(); A.fq = ctx->fq.as<double>(); A.Npad = T.Lg.Npad; A.nq = op.nq; A.b = bblk; A.overwrite = !accumulate;
         const unsigned gr = nblocks((long long)T.nctas * TP_MAXW * TP_K, 8);
-        if (op.nq == 1) tp_rhs_kernel<1><<<gr, 256, 0, ctx->stream>>>(A);
+        if (local) tp_rhs_local_kernel<<<gr, 256, 0, ctx->stream>>>(A);
+        else if (op.nq == 1) tp_rhs_kernel<1><<<gr, 256, 0, ctx->stream>>>(A);
         else if (op.nq == 3) tp_rhs_kernel<3><<<gr, 256, 0, ctx->stream>>>(A);
         else if (op.nq == 4) tp_rhs_kernel<4><<<gr, 256, 0, ctx->stream>>>(A);
         else if (op.nq == 6) tp_rhs_kernel<6><<<gr, 256, 0, ctx->stream>>>(A);
@@ -1669,6 +1704,7 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
         RhsLeftArgs A;
         A.nleft = T.nleft; A.leftcols = T.leftcols.as<int>(); A.adjptr = S.adjptr.as<long long>(); A.adjcell = S.adjcell.as<int>();
         A.adjloc = S.adjloc.as<unsigned char>(); A.fq = ctx->fq.as<double>(); A.Lg = T.Lg; A.nq = op.nq; A.b = bblk; A.overwrite = !accumulate;
+        A.local = local ? 1 : 0;
         tp_rhs_left_kernel<<<nblocks(T.nleft, 256), 256, 0, ctx->stream>>>(A);
         LAUNCHED(ctx);
     }
@@ -1909,6 +1945,8 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "template_permute_mesh")) { C->tmpl_permute_mesh = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_min_cols")) { C->tmpl_mincols = value < 1 ? 1 : value; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_class_mask")) { C->tmpl_classmask = value & 3; return EXTFEM_OK; }
+    if (key && !strcmp(key, "template_flat_writeout")) { C->tmpl_flat = std::max(value, 0); return EXTFEM_OK; }
+    if (key && !strcmp(key, "rhs_local")) { C->rhs_local = value != 0; return EXTFEM_OK; }
     return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("unknown option ") + (key ? key : "(null)"));
 }
 

@@ -1,0 +1,126 @@
+"""GPU parity tests of the second half of round 2: the cell-local form of the fast right-hand side (`rhs_local`) against
+the point-value form and the oracle, and the flat write-out of the walk kernel (`template_flat_writeout`) in overwrite and
+accumulate mode.  CUDA path through the C-ABI against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+
+from util import System, check_values, check_values_entrywise
+
+pytestmark = pytest.mark.gpu
+
+ID, GRAD = 0, 1
+
+
+def _grid(pkg, dim, n):
+    X = np.linspace(0, 1, n + 1)
+    if dim == 1:
+        return pkg.simplexgrid(np.linspace(0, 1, 8 * n + 1) ** 1.5)
+    if dim == 2:
+        return pkg.simplexgrid(X, X ** 2)
+    return pkg.simplexgrid(X, X ** 1.3, X)
+
+
+@pytest.mark.parametrize("dim,order,kernel,params,quadorder", [
+    (3, 2, "sincos301", [1.3], -1),      # config 2's right-hand side: 4-point rule, specialised kernel
+    (3, 2, "exp2x", [], 1),              # 1-point rule
+    (3, 1, "sincos301", [0.7], 2),       # P1 with the 4-point rule
+    (3, 2, "xy", [], 3),                 # 8 points
+    (2, 2, "xy", [], -1),                # 3-point rule
+    (2, 2, "sincos301", [1.0], 4),       # 9 points
+    (2, 1, "exp2x", [], 3),              # 4 points
+    (1, 2, "step105", [], 5),            # 3-point Gauss rule in 1D
+    (1, 2, "exp2x", [], 3),              # 2 points
+    (1, 1, "constant_one", [], -1),
+    (2, 2, "xy", [], 6),                 # 16 points: no compile-time kernel, the point-value form serves it
+])
+def test_rhs_local_form(pkg, ora, engine, dim, order, kernel, params, quadorder):
+    """Fast RHS, cell-local form (linear_operator.jl:618-633: local vector per cell, then one add per dof) with and without
+    templates, regions, accumulate; must agree with the oracle entrywise and with the point-value form to rounding."""
+    g = _grid(pkg, dim, 6 if dim == 3 else 12)
+    g.cellregions[::3] = 2
+    S = System(pkg, ora, engine, g, [pkg.H1Pk(1, dim, order)])
+    kw = dict(kernel_id=pkg.lib.kernel_id(kernel), params=params, factor=1.9)
+    if quadorder >= 0:
+        kw["quadorder"] = quadorder
+    okw = dict(params=params, factor=1.9)
+    if quadorder >= 0:
+        okw["quadorder"] = quadorder
+    got = {}
+    try:
+        for mincols in (2, 1 << 30):         # template plan | every column on the adjacency-list kernel
+            engine.set_option("template_min_cols", mincols)
+            S = System(pkg, ora, engine, g, [pkg.H1Pk(1, dim, order)])
+            for regions in ((), (2,)):
+                ref = np.zeros(S.N); sc = np.zeros(S.N)
+                ora.assemble_linear(S.omesh, S.oargs([(0, ID)]), ref, kernel, regions=list(regions), **okw)
+                with ora.abs_accumulate():
+                    ora.assemble_linear(S.omesh, S.oargs([(0, ID)]), sc, kernel, regions=list(regions), **okw)
+                for local in (1, 0):
+                    engine.set_option("rhs_local", local)
+                    d = engine.make_opdesc([(0, ID)], regions=regions, **kw)
+                    b = np.empty(S.N)
+                    engine.assemble_linear(S.pat, d, b_out=b)
+                    check_values(b, ref, what=f"rhs local={local} mincols={mincols} regions={regions}")
+                    check_values_entrywise(b, ref, sc, what=f"rhs entrywise local={local}")
+                    engine.assemble_linear(S.pat, d, accumulate=True, b_out=b)
+                    check_values(b, 2 * ref, what=f"rhs accumulate local={local}")
+                    got[(mincols, regions, local)] = b
+                check_values(got[(mincols, regions, 1)], got[(mincols, regions, 0)], what="local vs point-value form")
+    finally:
+        engine.set_option("rhs_local", 1)
+        engine.set_option("template_min_cols", 24)
+
+
+def test_rhs_local_tabulated(pkg, ora, engine):
+    """Host-tabulated integrand through the cell-local form (values indexed by the ORIGINAL cell number in the transposed order)."""
+    X = np.linspace(0, 1, 8)
+    g = pkg.simplexgrid(X, X, X)
+    engine.set_option("template_min_cols", 2)
+    try:
+        S = System(pkg, ora, engine, g, [pkg.H1P2(1, 3)])
+        desc = engine.make_opdesc([(0, ID)], kernel_id=pkg.lib.kernel_id("tabulated"))
+        xq = engine.quadrature_points_x(S.pat, desc, g.ncells, 3)
+        vals = (np.exp(xq[..., 0]) * xq[..., 1] + np.sin(3 * xq[..., 2]))[..., None]
+        desc = engine.make_opdesc([(0, ID)], kernel_id=pkg.lib.kernel_id("tabulated"), tabulated=vals)
+        ref = np.zeros(S.N)
+        ora.assemble_linear(S.omesh, S.oargs([(0, ID)]), ref, "tabulated", tabulated=vals)
+        for local in (1, 0):
+            engine.set_option("rhs_local", local)
+            b = np.empty(S.N)
+            engine.assemble_linear(S.pat, desc, b_out=b)
+            check_values(b, ref, what=f"tabulated rhs local={local}")
+    finally:
+        engine.set_option("rhs_local", 1)
+        engine.set_option("template_min_cols", 24)
+
+
+@pytest.mark.parametrize("n", [10, 13])
+def test_walk_flat_writeout(pkg, ora, engine, n):
+    """Walk kernel with the flat write-out (skewed accumulator columns): overwrite (first-touch) and accumulate mode against the
+    oracle, bit-identical to the position-per-lane write-out."""
+    X = np.linspace(0, 1, n + 1)
+    g = pkg.simplexgrid(X, X ** 1.2, X)
+    S = System(pkg, ora, engine, g, [pkg.H1P2(1, 3)])
+    desc = engine.make_opdesc([(0, GRAD)], [(0, GRAD)], factor=1.3)
+    ref = ora.assemble_bilinear(S.omesh, S.oargs([(0, GRAD)]), S.oargs([(0, GRAD)]), factor=1.3, csc=(S.colptr, S.rowval))
+    res = {}
+    try:
+        for flat in (0, 20, 1000):
+            engine.set_option("template_flat_writeout", flat)
+            nz = np.empty(S.rowval.size)
+            engine.assemble_bilinear(S.pat, desc, nzval_out=nz)
+            stats = engine.plan_stats(S.pat, 0)
+            assert stats["templates"] > 0
+            check_values(nz, ref, what=f"walk kernel flat={flat}")
+            res[flat] = nz.copy()
+            # accumulate on top of known values: the kernel first loads the column segments into its accumulators
+            base = np.linspace(-1.0, 1.0, S.rowval.size)
+            engine.values_set(S.pat, nzval=base, b=np.zeros(S.N))
+            engine.assemble_bilinear(S.pat, desc, accumulate=True, nzval_out=nz)
+            check_values(nz - base, ref, what=f"walk kernel accumulate flat={flat}")
+            engine.values_zero(S.pat, True, True)
+            engine.assemble_bilinear(S.pat, desc, accumulate=True, nzval_out=nz)
+            check_values(nz, ref, what=f"walk kernel zero + accumulate flat={flat}")
+        assert np.array_equal(res[0], res[20]) and np.array_equal(res[0], res[1000])
+    finally:
+        engine.set_option("template_flat_writeout", 0)
