@@ -157,6 +157,9 @@ struct Ctx {
     int tmpl_flat = 0;          // option "template_flat_writeout": the walk kernel writes columns of up to this many entries out over
                                 // the flat (column, position) index (0: none)
     bool rhs_local = true;      // option "rhs_local": fast right-hand side through cell-local vectors (one value per (dof, cell) pair)
+    bool rhs_fast_trig = true;  // option "rhs_fast_trig": sin / cos of the registered right-hand sides through tp_sin / tp_cos (fastplan.cuh)
+    int rhs_groups = 2;         // option "rhs_groups": column groups a warp of the cell-local gather serves at once (1, 2, 4)
+    int rhs_ahead = -1;         // option "rhs_prefetch_warps": prefetch distance of its descriptors in launch-order warps (-1: derived)
     bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator
     long long launches = 0;
     cudaStream_t stream2 = nullptr;   // exchange stream: the interface reduction of the matrix runs beside the rhs assembly
@@ -1672,7 +1675,8 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
         bool launched = false;
 #define RHS_LOCAL(D, N) \
         if (!launched && dim == D && op.nq == N) { \
-            if (op.kernel_id == EXTFEM_LIN_SINCOS301) tp_rhs_cell_local_kernel<D, N, EXTFEM_LIN_SINCOS301><<<gcell, 256, 0, ctx->stream>>>(CL); \
+            if (op.kernel_id == EXTFEM_LIN_SINCOS301 && ctx->rhs_fast_trig) tp_rhs_cell_local_kernel<D, N, TP_KID_SINCOS301_FT><<<gcell, 256, 0, ctx->stream>>>(CL); \
+            else if (op.kernel_id == EXTFEM_LIN_SINCOS301) tp_rhs_cell_local_kernel<D, N, EXTFEM_LIN_SINCOS301><<<gcell, 256, 0, ctx->stream>>>(CL); \
             else tp_rhs_cell_local_kernel<D, N, -1><<<gcell, 256, 0, ctx->stream>>>(CL); \
             launched = true; \
         }
@@ -1692,7 +1696,12 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
         A.nwarps = T.nctas * TP_MAXW; A.wdesc = T.wdesc.as<int4>(); A.slotcol = T.slotcol.as<int>(); A.slotpb = T.slotpb.as<int>();
         A.tmpl = T.tmpl.as<unsigned>(); A.fq = ctx->fq.as<double>(); A.Npad = T.Lg.Npad; A.nq = op.nq; A.b = bblk; A.overwrite = !accumulate;
         const unsigned gr = nblocks((long long)T.nctas * TP_MAXW * TP_K, 8);
-        if (local) tp_rhs_local_kernel<<<gr, 256, 0, ctx->stream>>>(A);
+        // descriptors are prefetched about one and a half waves of resident warps ahead
+        const int G = ctx->rhs_groups >= 4 ? 4 : ctx->rhs_groups >= 2 ? 2 : 1;
+        A.ahead = ctx->rhs_ahead >= 0 ? ctx->rhs_ahead : ctx->sm_count * 48 * G;
+        if (local && ctx->rhs_groups >= 4) tp_rhs_local_kernel<4><<<nblocks((long long)A.nwarps, 32), 256, 0, ctx->stream>>>(A);
+        else if (local && ctx->rhs_groups >= 2) tp_rhs_local_kernel<2><<<nblocks((long long)A.nwarps, 16), 256, 0, ctx->stream>>>(A);
+        else if (local) tp_rhs_local_kernel<1><<<gr, 256, 0, ctx->stream>>>(A);
         else if (op.nq == 1) tp_rhs_kernel<1><<<gr, 256, 0, ctx->stream>>>(A);
         else if (op.nq == 3) tp_rhs_kernel<3><<<gr, 256, 0, ctx->stream>>>(A);
         else if (op.nq == 4) tp_rhs_kernel<4><<<gr, 256, 0, ctx->stream>>>(A);
@@ -1947,6 +1956,9 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "template_class_mask")) { C->tmpl_classmask = value & 3; return EXTFEM_OK; }
     if (key && !strcmp(key, "template_flat_writeout")) { C->tmpl_flat = std::max(value, 0); return EXTFEM_OK; }
     if (key && !strcmp(key, "rhs_local")) { C->rhs_local = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "rhs_prefetch_warps")) { C->rhs_ahead = value; return EXTFEM_OK; }
+    if (key && !strcmp(key, "rhs_fast_trig")) { C->rhs_fast_trig = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "rhs_groups")) { C->rhs_groups = std::min(std::max(value, 1), 4); return EXTFEM_OK; }
     return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("unknown option ") + (key ? key : "(null)"));
 }
 

@@ -55,8 +55,9 @@ def test_rhs_local_form(pkg, ora, engine, dim, order, kernel, params, quadorder)
                 ora.assemble_linear(S.omesh, S.oargs([(0, ID)]), ref, kernel, regions=list(regions), **okw)
                 with ora.abs_accumulate():
                     ora.assemble_linear(S.omesh, S.oargs([(0, ID)]), sc, kernel, regions=list(regions), **okw)
-                for local in (1, 0):
+                for local, groups in ((1, 2), (1, 1), (1, 4), (0, 2)):
                     engine.set_option("rhs_local", local)
+                    engine.set_option("rhs_groups", groups)      # column groups a warp of the cell-local gather serves at once
                     d = engine.make_opdesc([(0, ID)], regions=regions, **kw)
                     b = np.empty(S.N)
                     engine.assemble_linear(S.pat, d, b_out=b)
@@ -64,10 +65,13 @@ def test_rhs_local_form(pkg, ora, engine, dim, order, kernel, params, quadorder)
                     check_values_entrywise(b, ref, sc, what=f"rhs entrywise local={local}")
                     engine.assemble_linear(S.pat, d, accumulate=True, b_out=b)
                     check_values(b, 2 * ref, what=f"rhs accumulate local={local}")
-                    got[(mincols, regions, local)] = b
-                check_values(got[(mincols, regions, 1)], got[(mincols, regions, 0)], what="local vs point-value form")
+                    got[(mincols, regions, local, groups)] = b
+                check_values(got[(mincols, regions, 1, 2)], got[(mincols, regions, 0, 2)], what="local vs point-value form")
+                for groups in (1, 4):
+                    assert np.array_equal(got[(mincols, regions, 1, 2)], got[(mincols, regions, 1, groups)])
     finally:
         engine.set_option("rhs_local", 1)
+        engine.set_option("rhs_groups", 2)
         engine.set_option("template_min_cols", 24)
 
 
@@ -124,3 +128,32 @@ def test_walk_flat_writeout(pkg, ora, engine, n):
         assert np.array_equal(res[0], res[20]) and np.array_equal(res[0], res[1000])
     finally:
         engine.set_option("template_flat_writeout", 0)
+
+
+@pytest.mark.parametrize("scale,shift", [(1.0, 0.0), (130.0, -70.0), (3.0, 2.0e6)])
+def test_rhs_fast_trig_ranges(pkg, ora, engine, scale, shift):
+    """sin / cos of the cell kernel (tp_sin / tp_cos: Cody-Waite reduction + fdlibm kernels) against the oracle's libm on meshes
+    whose coordinates give arguments of a few units, of several hundred (many quadrants, both signs) and beyond 2^20 (library
+    fallback); and against the library functions on the device (option rhs_fast_trig = 0)."""
+    X = np.linspace(0, 1, 8)
+    g = pkg.simplexgrid(X * scale + shift, X ** 1.1 * scale + shift, X)
+    S = System(pkg, ora, engine, g, [pkg.H1P2(1, 3)])
+    ref = np.zeros(S.N); sc = np.zeros(S.N)
+    ora.assemble_linear(S.omesh, S.oargs([(0, ID)]), ref, "sincos301", params=[0.8])
+    with ora.abs_accumulate():
+        ora.assemble_linear(S.omesh, S.oargs([(0, ID)]), sc, "sincos301", params=[0.8])
+    d = engine.make_opdesc([(0, ID)], kernel_id=pkg.lib.kernel_id("sincos301"), params=[0.8])
+    got = {}
+    # the oracle evaluates x_q in another order: an ulp of the coordinates changes the argument of sin / cos by 3.9 ulp(|x|), so the
+    # comparison with the oracle is scaled by the coordinate size; device library vs tp_sin / tp_cos see identical arguments
+    loose = 1e-12 * max(1.0, 40.0 * float(np.abs(g.coords).max()))
+    try:
+        for ft in (1, 0):
+            engine.set_option("rhs_fast_trig", ft)
+            b = np.empty(S.N)
+            engine.assemble_linear(S.pat, d, b_out=b)
+            check_values_entrywise(b, ref, sc, rtol=loose, what=f"rhs fast_trig={ft} scale={scale} shift={shift}")
+            got[ft] = b
+        check_values_entrywise(got[1], got[0], sc, rtol=1e-12, what="tp_sin/tp_cos vs library sin/cos")
+    finally:
+        engine.set_option("rhs_fast_trig", 1)
