@@ -158,7 +158,8 @@ struct Ctx {
                                 // the flat (column, position) index (0: none)
     bool rhs_local = true;      // option "rhs_local": fast right-hand side through cell-local vectors (one value per (dof, cell) pair)
     bool rhs_fast_trig = true;  // option "rhs_fast_trig": sin / cos of the registered right-hand sides through tp_sin / tp_cos (fastplan.cuh)
-    int rhs_groups = 2;         // option "rhs_groups": column groups a warp of the cell-local gather serves at once (1, 2, 4)
+    int rhs_gather_ctas = 5;    // option "rhs_gather_ctas": resident CTAs per SM the cell-local gather is compiled for (5, 6, 8)
+    int rhs_groups = 1;         // option "rhs_groups": column groups a warp of the cell-local gather serves at once (1, 2, 4)
     int rhs_ahead = -1;         // option "rhs_prefetch_warps": prefetch distance of its descriptors in launch-order warps (-1: derived)
     bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator
     long long launches = 0;
@@ -1643,7 +1644,7 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
     if (int rca = const_acquire(ctx)) return rca;
     EXTFEM_CUDA_CHECK(ctx, cudaMemcpyToSymbolAsync(c_tp_phi, phi.data(), phi.size() * 8, 0, cudaMemcpyHostToDevice, ctx->stream));
     // cell-local form (one plane per local dof) for the rules with a compile-time kernel, else point values (one plane per point)
-    const bool local = ctx->rhs_local && rhs_local_rule(dim, op.nq);
+    const bool local = ctx->rhs_local && rhs_local_rule(dim, op.nq) && ns == (S.order == 1 ? dim + 1 : (dim + 1) * (dim + 2) / 2);
     if (int rc = ensure(ctx, ctx->fq, (size_t)T.Lg.Npad * (local ? ns : op.nq) * 8)) return rc;
     double *bblk = P.b.as<double>() + P.rowoff[b];
     if (!accumulate && P.rowspaces.size() > 1) {
@@ -1673,16 +1674,17 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
             for (int r = 0; r < dim; ++r) CL.qx[q * dim + r] = Q.x[(size_t)q * dim + r];
         }
         bool launched = false;
-#define RHS_LOCAL(D, N) \
-        if (!launched && dim == D && op.nq == N) { \
-            if (op.kernel_id == EXTFEM_LIN_SINCOS301 && ctx->rhs_fast_trig) tp_rhs_cell_local_kernel<D, N, TP_KID_SINCOS301_FT><<<gcell, 256, 0, ctx->stream>>>(CL); \
-            else if (op.kernel_id == EXTFEM_LIN_SINCOS301) tp_rhs_cell_local_kernel<D, N, EXTFEM_LIN_SINCOS301><<<gcell, 256, 0, ctx->stream>>>(CL); \
-            else tp_rhs_cell_local_kernel<D, N, -1><<<gcell, 256, 0, ctx->stream>>>(CL); \
+#define RHS_LOCAL(D, N, S) \
+        if (!launched && dim == D && op.nq == N && ns == S) { \
+            if (op.kernel_id == EXTFEM_LIN_SINCOS301 && ctx->rhs_fast_trig) tp_rhs_cell_local_kernel<D, N, S, TP_KID_SINCOS301_FT><<<gcell, 256, 0, ctx->stream>>>(CL); \
+            else tp_rhs_cell_local_kernel<D, N, S, -1><<<gcell, 256, 0, ctx->stream>>>(CL); \
             launched = true; \
         }
-        RHS_LOCAL(1, 1) RHS_LOCAL(1, 2) RHS_LOCAL(1, 3) RHS_LOCAL(1, 4)
-        RHS_LOCAL(2, 1) RHS_LOCAL(2, 3) RHS_LOCAL(2, 4) RHS_LOCAL(2, 9)
-        RHS_LOCAL(3, 1) RHS_LOCAL(3, 4) RHS_LOCAL(3, 8)
+#define RHS_LOCAL2(D, N, S1, S2) RHS_LOCAL(D, N, S1) RHS_LOCAL(D, N, S2)
+        RHS_LOCAL2(1, 1, 2, 3) RHS_LOCAL2(1, 2, 2, 3) RHS_LOCAL2(1, 3, 2, 3) RHS_LOCAL2(1, 4, 2, 3)
+        RHS_LOCAL2(2, 1, 3, 6) RHS_LOCAL2(2, 3, 3, 6) RHS_LOCAL2(2, 4, 3, 6) RHS_LOCAL2(2, 9, 3, 6)
+        RHS_LOCAL2(3, 1, 4, 10) RHS_LOCAL2(3, 4, 4, 10) RHS_LOCAL2(3, 8, 4, 10)
+#undef RHS_LOCAL2
 #undef RHS_LOCAL
         if (!launched) return fail(ctx, EXTFEM_ERR_CAPACITY, "fast right-hand side: no cell kernel for this rule");
     }
@@ -1699,9 +1701,11 @@ static int try_fast_linear(Ctx *ctx, Pattern &P, const Prepared &R, const extfem
         // descriptors are prefetched about one and a half waves of resident warps ahead
         const int G = ctx->rhs_groups >= 4 ? 4 : ctx->rhs_groups >= 2 ? 2 : 1;
         A.ahead = ctx->rhs_ahead >= 0 ? ctx->rhs_ahead : ctx->sm_count * 48 * G;
-        if (local && ctx->rhs_groups >= 4) tp_rhs_local_kernel<4><<<nblocks((long long)A.nwarps, 32), 256, 0, ctx->stream>>>(A);
-        else if (local && ctx->rhs_groups >= 2) tp_rhs_local_kernel<2><<<nblocks((long long)A.nwarps, 16), 256, 0, ctx->stream>>>(A);
-        else if (local) tp_rhs_local_kernel<1><<<gr, 256, 0, ctx->stream>>>(A);
+        if (local && ctx->rhs_groups >= 4) tp_rhs_local_kernel<4, 2><<<nblocks((long long)A.nwarps, 32), 256, 0, ctx->stream>>>(A);
+        else if (local && ctx->rhs_groups >= 2) tp_rhs_local_kernel<2, 4><<<nblocks((long long)A.nwarps, 16), 256, 0, ctx->stream>>>(A);
+        else if (local && ctx->rhs_gather_ctas >= 8) tp_rhs_local_kernel<1, 8><<<gr, 256, 0, ctx->stream>>>(A);
+        else if (local && ctx->rhs_gather_ctas >= 6) tp_rhs_local_kernel<1, 6><<<gr, 256, 0, ctx->stream>>>(A);
+        else if (local) tp_rhs_local_kernel<1, 5><<<gr, 256, 0, ctx->stream>>>(A);
         else if (op.nq == 1) tp_rhs_kernel<1><<<gr, 256, 0, ctx->stream>>>(A);
         else if (op.nq == 3) tp_rhs_kernel<3><<<gr, 256, 0, ctx->stream>>>(A);
         else if (op.nq == 4) tp_rhs_kernel<4><<<gr, 256, 0, ctx->stream>>>(A);
@@ -1958,6 +1962,7 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "rhs_local")) { C->rhs_local = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "rhs_prefetch_warps")) { C->rhs_ahead = value; return EXTFEM_OK; }
     if (key && !strcmp(key, "rhs_fast_trig")) { C->rhs_fast_trig = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "rhs_gather_ctas")) { C->rhs_gather_ctas = value; return EXTFEM_OK; }
     if (key && !strcmp(key, "rhs_groups")) { C->rhs_groups = std::min(std::max(value, 1), 4); return EXTFEM_OK; }
     return fail(C, EXTFEM_ERR_BAD_ARGUMENT, std::string("unknown option ") + (key ? key : "(null)"));
 }

@@ -55,9 +55,11 @@ def test_rhs_local_form(pkg, ora, engine, dim, order, kernel, params, quadorder)
                 ora.assemble_linear(S.omesh, S.oargs([(0, ID)]), ref, kernel, regions=list(regions), **okw)
                 with ora.abs_accumulate():
                     ora.assemble_linear(S.omesh, S.oargs([(0, ID)]), sc, kernel, regions=list(regions), **okw)
-                for local, groups in ((1, 2), (1, 1), (1, 4), (0, 2)):
+                # (cell-local form, column groups a warp of its gather serves at once, occupancy variant of the one-group gather)
+                for local, groups, ctas in ((1, 1, 5), (1, 2, 5), (1, 4, 5), (1, 1, 6), (1, 1, 8), (0, 1, 5)):
                     engine.set_option("rhs_local", local)
-                    engine.set_option("rhs_groups", groups)      # column groups a warp of the cell-local gather serves at once
+                    engine.set_option("rhs_groups", groups)
+                    engine.set_option("rhs_gather_ctas", ctas)
                     d = engine.make_opdesc([(0, ID)], regions=regions, **kw)
                     b = np.empty(S.N)
                     engine.assemble_linear(S.pat, d, b_out=b)
@@ -65,13 +67,14 @@ def test_rhs_local_form(pkg, ora, engine, dim, order, kernel, params, quadorder)
                     check_values_entrywise(b, ref, sc, what=f"rhs entrywise local={local}")
                     engine.assemble_linear(S.pat, d, accumulate=True, b_out=b)
                     check_values(b, 2 * ref, what=f"rhs accumulate local={local}")
-                    got[(mincols, regions, local, groups)] = b
-                check_values(got[(mincols, regions, 1, 2)], got[(mincols, regions, 0, 2)], what="local vs point-value form")
-                for groups in (1, 4):
-                    assert np.array_equal(got[(mincols, regions, 1, 2)], got[(mincols, regions, 1, groups)])
+                    got[(local, groups, ctas)] = b
+                check_values(got[(1, 1, 5)], got[(0, 1, 5)], what="local vs point-value form")
+                for key in ((1, 2, 5), (1, 4, 5), (1, 1, 6), (1, 1, 8)):
+                    assert np.array_equal(got[(1, 1, 5)], got[key]), key
     finally:
         engine.set_option("rhs_local", 1)
-        engine.set_option("rhs_groups", 2)
+        engine.set_option("rhs_groups", 1)
+        engine.set_option("rhs_gather_ctas", 5)
         engine.set_option("template_min_cols", 24)
 
 
