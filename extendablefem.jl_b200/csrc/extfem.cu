@@ -158,7 +158,8 @@ struct Ctx {
                                 // the flat (column, position) index (0: none)
     bool rhs_local = true;      // option "rhs_local": fast right-hand side through cell-local vectors (one value per (dof, cell) pair)
     bool rhs_fast_trig = true;  // option "rhs_fast_trig": sin / cos of the registered right-hand sides through tp_sin / tp_cos (fastplan.cuh)
-    int rhs_gather_ctas = 5;    // option "rhs_gather_ctas": resident CTAs per SM the cell-local gather is compiled for (5, 6, 8)
+    int rhs_gather_ctas = 8;    // option "rhs_gather_ctas": resident CTAs per SM the cell-local gather is compiled for (5, 6, 8): it is
+                                // latency-bound, full occupancy (32 registers) wins over the few spilled bytes it costs
     int rhs_groups = 1;         // option "rhs_groups": column groups a warp of the cell-local gather serves at once (1, 2, 4)
     int rhs_ahead = -1;         // option "rhs_prefetch_warps": prefetch distance of its descriptors in launch-order warps (-1: derived)
     bool bary_enabled = true;   // option "fastpath_closed_form": 0 keeps the table evaluator

@@ -56,7 +56,7 @@ def test_rhs_local_form(pkg, ora, engine, dim, order, kernel, params, quadorder)
                 with ora.abs_accumulate():
                     ora.assemble_linear(S.omesh, S.oargs([(0, ID)]), sc, kernel, regions=list(regions), **okw)
                 # (cell-local form, column groups a warp of its gather serves at once, occupancy variant of the one-group gather)
-                for local, groups, ctas in ((1, 1, 5), (1, 2, 5), (1, 4, 5), (1, 1, 6), (1, 1, 8), (0, 1, 5)):
+                for local, groups, ctas in ((1, 1, 8), (1, 2, 8), (1, 4, 8), (1, 1, 6), (1, 1, 5), (0, 1, 8)):
                     engine.set_option("rhs_local", local)
                     engine.set_option("rhs_groups", groups)
                     engine.set_option("rhs_gather_ctas", ctas)
@@ -68,13 +68,13 @@ def test_rhs_local_form(pkg, ora, engine, dim, order, kernel, params, quadorder)
                     engine.assemble_linear(S.pat, d, accumulate=True, b_out=b)
                     check_values(b, 2 * ref, what=f"rhs accumulate local={local}")
                     got[(local, groups, ctas)] = b
-                check_values(got[(1, 1, 5)], got[(0, 1, 5)], what="local vs point-value form")
-                for key in ((1, 2, 5), (1, 4, 5), (1, 1, 6), (1, 1, 8)):
-                    assert np.array_equal(got[(1, 1, 5)], got[key]), key
+                check_values(got[(1, 1, 8)], got[(0, 1, 8)], what="local vs point-value form")
+                for key in ((1, 2, 8), (1, 4, 8), (1, 1, 6), (1, 1, 5)):
+                    assert np.array_equal(got[(1, 1, 8)], got[key]), key
     finally:
         engine.set_option("rhs_local", 1)
         engine.set_option("rhs_groups", 1)
-        engine.set_option("rhs_gather_ctas", 5)
+        engine.set_option("rhs_gather_ctas", 8)
         engine.set_option("template_min_cols", 24)
 
 
