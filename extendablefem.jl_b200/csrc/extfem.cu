@@ -96,6 +96,7 @@ struct Pattern {
     DevBuf colptr, rowval, nzval, b;
     DevBuf lstart, lcolptr, lpack;             // lower-triangle export (extfem_values_get_lower): suffix starts, packed colptr, staging
     long long nnz_lower = -1;
+    std::vector<long long> lchunk_col, lchunk_off;   // column chunks of the pipelined export and the packed offsets at their ends
     std::vector<std::unique_ptr<DevBuf>> posmap; // per column block
     DevBuf chunkptr;
     int nchunks = 0;
@@ -167,6 +168,7 @@ struct Ctx {
     cudaStream_t stream2 = nullptr;   // exchange stream: the interface reduction of the matrix runs beside the rhs assembly
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool aux_pending = false;         // work on stream2 that later calls on the main stream must wait for
+    cudaEvent_t cev[8] = {};          // chunk events of the pipelined lower-triangle export (created on first use)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t uev[16] = {};
     double last_ms[3] = {0, 0, 0};
@@ -1890,6 +1892,7 @@ int extfem_ctx_destroy(extfem_ctx *ctx)
     cudaStreamSynchronize(C->stream);
     for (auto &ev : C->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : C->uev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : C->cev) if (ev) cudaEventDestroy(ev);
     if (C->stream2) { cudaStreamSynchronize(C->stream2); cudaStreamDestroy(C->stream2); }
     if (C->ev_fork) cudaEventDestroy(C->ev_fork);
     if (C->ev_join) cudaEventDestroy(C->ev_join);
@@ -2642,6 +2645,14 @@ static int ensure_lower(Ctx *C, Pattern &P)
     EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(&n, P.lcolptr.as<long long>() + P.ncols, 8, cudaMemcpyDeviceToHost, C->stream));
     EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
     P.nnz_lower = n;
+    // column chunks of the pipelined export (extfem_values_get_lower): packed offsets at the chunk ends
+    const int nch = n > (1ll << 22) ? 8 : 1;
+    P.lchunk_col.assign(nch + 1, 0); P.lchunk_off.assign(nch + 1, 0);
+    for (int k = 0; k <= nch; ++k) {
+        P.lchunk_col[k] = P.ncols * k / nch;
+        EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(&P.lchunk_off[k], P.lcolptr.as<long long>() + P.lchunk_col[k], 8, cudaMemcpyDeviceToHost, C->stream));
+    }
+    EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
     return EXTFEM_OK;
 }
 
@@ -2660,8 +2671,8 @@ int extfem_pattern_get_lower(extfem_ctx *ctx, int pattern, int64_t *nnz_lower, i
     }
     if (rowval) {
         if (int rc = ensure(C, r64, (size_t)std::max<long long>(P.nnz_lower, 1) * 8)) return rc;
-        lower_pack_kernel<int, long long><<<nblocks(P.ncols * 32, 256), 256, 0, C->stream>>>(P.ncols, P.lstart.as<long long>(), P.lcolptr.as<long long>(),
-                                                                                           P.rowval.as<int>(), r64.as<long long>(), 1LL);
+        lower_pack_kernel<int, long long, 8><<<nblocks(P.ncols * 8, 256), 256, 0, C->stream>>>(0, P.ncols, P.lstart.as<long long>(), P.lcolptr.as<long long>(),
+                                                                                             P.rowval.as<int>(), r64.as<long long>(), 1LL);
         LAUNCHED(C);
         EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(rowval, r64.p, (size_t)P.nnz_lower * 8, cudaMemcpyDefault, C->stream));
     }
@@ -2674,14 +2685,36 @@ int extfem_values_get_lower(extfem_ctx *ctx, int pattern, double *nzval_lower, d
     CTX_GUARD(ctx);
     GET_PATTERN(pattern);
     if (int rc = ensure_lower(C, P)) return rc;
+    // pack kernels of column chunks on the main stream, the copy of a chunk on the exchange stream as soon as it is packed: the
+    // packing hides behind the PCIe transfer (one chunk for small systems)
+    const int nch = nzval_lower ? (int)P.lchunk_col.size() - 1 : 0;
+    const bool piped = nch > 1 && C->stream2;
+    if (piped) {
+        for (int k = 0; k < nch; ++k)
+            if (!C->cev[k]) EXTFEM_CUDA_CHECK(C, cudaEventCreateWithFlags(&C->cev[k], cudaEventDisableTiming));
+        EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->ev_fork, C->stream));
+        EXTFEM_CUDA_CHECK(C, cudaStreamWaitEvent(C->stream2, C->ev_fork, 0));
+    }
+    cudaStream_t cs = piped ? C->stream2 : C->stream;
+    if (b && piped) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, cs));
     if (nzval_lower) {
         if (int rc = ensure(C, P.lpack, (size_t)std::max<long long>(P.nnz_lower, 1) * 8)) return rc;
-        lower_pack_kernel<double, double><<<nblocks(P.ncols * 32, 256), 256, 0, C->stream>>>(P.ncols, P.lstart.as<long long>(), P.lcolptr.as<long long>(),
-                                                                                           P.nzval.as<double>(), P.lpack.as<double>(), 0.0);
-        LAUNCHED(C);
-        EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(nzval_lower, P.lpack.p, (size_t)P.nnz_lower * 8, cudaMemcpyDefault, C->stream));
+        for (int k = 0; k < nch; ++k) {
+            const long long c0 = P.lchunk_col[k], c1 = P.lchunk_col[k + 1], o0 = P.lchunk_off[k], o1 = P.lchunk_off[k + 1];
+            if (c1 > c0) {
+                lower_pack_kernel<double, double, 8><<<nblocks((c1 - c0) * 8, 256), 256, 0, C->stream>>>(
+                    c0, c1, P.lstart.as<long long>(), P.lcolptr.as<long long>(), P.nzval.as<double>(), P.lpack.as<double>(), 0.0);
+                LAUNCHED(C);
+            }
+            if (piped) {
+                EXTFEM_CUDA_CHECK(C, cudaEventRecord(C->cev[k], C->stream));
+                EXTFEM_CUDA_CHECK(C, cudaStreamWaitEvent(cs, C->cev[k], 0));
+            }
+            if (o1 > o0) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(nzval_lower + o0, P.lpack.as<double>() + o0, (size_t)(o1 - o0) * 8, cudaMemcpyDefault, cs));
+        }
     }
-    if (b) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    if (b && !piped) EXTFEM_CUDA_CHECK(C, cudaMemcpyAsync(b, P.b.p, (size_t)P.nrows * 8, cudaMemcpyDefault, C->stream));
+    if (piped) EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream2));
     EXTFEM_CUDA_CHECK(C, cudaStreamSynchronize(C->stream));
     return EXTFEM_OK;
 }

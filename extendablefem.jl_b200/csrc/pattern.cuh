@@ -226,16 +226,19 @@ __global__ void lower_start_kernel(long long ncols, const long long *__restrict_
     lstart[j] = lo; lcount[j] = end - lo;
 }
 
-// one warp per column: out[lcolptr[j] + k] = src[lstart[j] + k]  (values: T = double; row indices: int -> 1-based int64)
-template <typename TI, typename TO>
-__global__ void lower_pack_kernel(long long ncols, const long long *__restrict__ lstart, const long long *__restrict__ lcolptr,
-                                  const TI *__restrict__ src, TO *__restrict__ out, TO add)
+// LPC lanes per column of [c0, c1): out[lcolptr[j] + k] = src[lstart[j] + k]  (values: T = double; row indices: int -> 1-based
+// int64).  The lower part of a P2 column holds 10 to 33 entries: 8 lanes per column keep the lanes busy and let one warp run
+// four independent (start, offset) -> copy chains; consecutive columns are adjacent in `out`.
+template <typename TI, typename TO, int LPC>
+__global__ void __launch_bounds__(256) lower_pack_kernel(long long c0, long long c1, const long long *__restrict__ lstart,
+                                                         const long long *__restrict__ lcolptr, const TI *__restrict__ src,
+                                                         TO *__restrict__ out, TO add)
 {
-    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (j >= ncols) return;
+    const long long j = c0 + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPC;
+    const int lane = threadIdx.x % LPC;
+    if (j >= c1) return;
     const long long s = lstart[j], o = lcolptr[j], n = lcolptr[j + 1] - o;
-    for (long long k = lane; k < n; k += 32) out[o + k] = (TO)src[s + k] + add;
+    for (long long k = lane; k < n; k += LPC) out[o + k] = (TO)src[s + k] + add;
 }
 
 __global__ void add_one_kernel(long long n, const long long *__restrict__ in, long long *__restrict__ out)

@@ -160,3 +160,28 @@ def test_rhs_fast_trig_ranges(pkg, ora, engine, scale, shift):
         check_values_entrywise(got[1], got[0], sc, rtol=1e-12, what="tp_sin/tp_cos vs library sin/cos")
     finally:
         engine.set_option("rhs_fast_trig", 1)
+
+
+def test_lower_triangle_export_pipelined(pkg, engine):
+    """extfem_values_get_lower on a system large enough for the pipelined export (more than 2^22 lower entries: eight column chunks,
+    packed on the main stream and copied on the exchange stream): bit-identical to scipy's tril of the full copy-back; twice, into
+    pinned and pageable host arrays."""
+    import scipy.sparse as sp
+    import torch
+    X = np.linspace(0, 1, 36)
+    g = pkg.simplexgrid(X, X ** 1.1, X)
+    F = pkg.FESpace(pkg.H1P2(1, 3), g)
+    mesh = engine.mesh_set(g.coords, g.cellnodes, g.cellregions, g.cellvolumes)
+    pat = engine.pattern_build([engine.space_set(mesh, F.fetype.fe_id, 1, F.celldofs, F.ndofs)])
+    colptr, rowval = engine.pattern_get(pat)
+    engine.assemble_bilinear(pat, engine.make_opdesc([(0, GRAD)], [(0, GRAD)], factor=0.7))
+    engine.assemble_linear(pat, engine.make_opdesc([(0, ID)], kernel_id=pkg.lib.kernel_id("sincos301"), params=[1.0]))
+    nz, b = engine.values_get(pat)
+    L = sp.tril(sp.csc_matrix((nz, rowval - 1, colptr - 1), shape=(F.ndofs, F.ndofs)), format="csc")
+    n, cp, rv = engine.pattern_get_lower(pat)
+    assert n == L.nnz > (1 << 22) and np.array_equal(cp - 1, L.indptr) and np.array_equal(rv - 1, L.indices)
+    lz, lb = engine.values_get_lower(pat)
+    assert np.array_equal(lz, L.data) and np.array_equal(lb, b)
+    lz_pin = torch.empty(n, dtype=torch.float64).pin_memory(); lb_pin = torch.empty(F.ndofs, dtype=torch.float64).pin_memory()
+    engine.values_get_lower(pat, nzval_out=lz_pin, b_out=lb_pin)
+    assert np.array_equal(lz_pin.numpy(), L.data) and np.array_equal(lb_pin.numpy(), b)
