@@ -235,7 +235,9 @@ int extfem_values_set(extfem_ctx *ctx, int pattern, const double *nzval /*NULL o
 /* Symmetric forms: only the lower triangle crosses PCIe (half the bytes of extfem_values_get).  Rows are sorted per column, so
  * the entries with row >= column are a suffix of every column; they are packed on the device in column order.  The Julia side
  * wraps the result as Symmetric(SparseMatrixCSC(n, n, colptr, rowval, nzval), :L) -- what CHOLMOD / a CG need of an SPD matrix.
- * pattern_get_lower: nnz_lower, colptr [ncols+1] and rowval [nnz_lower] (Int64, 1-based; any of them may be NULL).           */
+ * pattern_get_lower: nnz_lower, colptr [ncols+1] and rowval [nnz_lower] (Int64, 1-based; any of them may be NULL).
+ * values_get_lower packs column chunks on the context's stream and copies every chunk on its exchange stream as soon as it is
+ * packed (pinned host arrays make the copies asynchronous); it returns when both arrays are complete.                          */
 int extfem_pattern_get_lower(extfem_ctx *ctx, int pattern, int64_t *nnz_lower, int64_t *colptr, int64_t *rowval);
 int extfem_values_get_lower(extfem_ctx *ctx, int pattern, double *nzval_lower /*[nnz_lower], NULL ok*/, double *b /*NULL ok*/);
 /* raw device pointers (colptr int64 0-based, rowval int32 0-based, nzval, b) for zero-copy users */
