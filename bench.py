@@ -301,7 +301,11 @@ def run_ours(args):
     nz_h = torch.empty(nnz, dtype=torch.float64).pin_memory()
     lz_h = torch.empty(nnz_lower, dtype=torch.float64).pin_memory()
     b_h = torch.empty(nrows, dtype=torch.float64).pin_memory()
-    vol_h = torch.from_numpy(np.ascontiguousarray(sh.cellvolumes)).pin_memory()
+    # one GPU: only the coordinates cross PCIe, the engine derives the cell volumes from them on the device (cellvolumes = NULL in
+    # extfem_mesh_update_coords); sharded: the host passes the volumes, because they carry the zero-volume ghost layer
+    vol_h = torch.from_numpy(np.ascontiguousarray(sh.cellvolumes)).pin_memory() if world > 1 else None
+    h2d_bytes = int(coords_h.numel() * 8 + (vol_h.numel() * 8 if vol_h is not None else 0))
+    nz_resident = eng.values_get(pat, want_b=False)[0] if (world == 1 and not args.no_parity) else None   # host volumes, checked above
     e2e_steps = max(1, min(args.steps, 3))
 
     def step_e2e(lower):
@@ -331,6 +335,10 @@ def run_ours(args):
     ms_e2e_full = time_e2e(False)
     ms_e2e = time_e2e(True)
     checksum = float(nz_h.sum())   # stiffness matrix annihilates constants: sum of all entries ~ 0 (single GPU)
+    e2e_vs_resident = None         # the e2e result (device-derived volumes) against the parity-checked resident matrix of the timed run
+    if nz_resident is not None:
+        e2e_vs_resident = float(np.abs(nz_h.numpy() - nz_resident).max() / np.abs(nz_resident).max())
+        del nz_resident
 
     # ---- device-resident solve (the path north_star describes): coordinates in, assemble, penalties, Jacobi-CG to 1e-10 on the
     # GPU, only x back (single GPU; config 5 is the multi-GPU version of this)
@@ -352,7 +360,7 @@ def run_ours(args):
         xs, its, rr = eng.cg(pat, rtol=1e-10, maxit=5000)
         t2 = time.perf_counter()
         resident = {"ms_coords_in_to_system_ready": (t1 - t0) * 1e3, "cg_iterations": int(its), "relres": float(rr), "ms_cg": (t2 - t1) * 1e3,
-                    "ms_total": (t2 - t0) * 1e3, "h2d_bytes": int(coords_h.numel() * 8 + vol_h.numel() * 8 + onb.size * 8), "d2h_bytes": int(nrows * 8),
+                    "ms_total": (t2 - t0) * 1e3, "h2d_bytes": int(h2d_bytes + onb.size * 8), "d2h_bytes": int(nrows * 8),
                     "max_abs_solution": float(np.abs(xs).max()),
                     "note": "homogeneous Dirichlet data on the cube boundary by penalties, Jacobi-CG until |r| <= 1e-10 |r0|; wall clock"}
 
@@ -404,10 +412,11 @@ def run_ours(args):
                          "kernel": "stiffness assembly kernels of rank 0 (geometry + owner-computes gather)", "kernel_ms": dom_ms,
                          "algorithmic_bytes": alg, "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(coords_h.numel() * 8 + vol_h.numel() * 8),
+                    "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(lz_h.numel() * 8 + b_h.numel() * 8),
-                    "variant": "C-ABI calls with pinned host buffers: coordinates + volumes in, lower triangle of the symmetric matrix "
-                               "(extfem_values_get_lower) + rhs out"},
+                    "variant": ("C-ABI calls with pinned host buffers: coordinates in" + (" (cell volumes derived on the device)" if vol_h is None
+                                else " + cell volumes (zero-volume ghost layer)") + ", lower triangle of the symmetric matrix "
+                                "(extfem_values_get_lower, packed in column chunks behind the copy) + rhs out")},
             "e2e_variants": {"full_copy_back": {"value": cells_total / (ms_e2e_full * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_full,
                                                 "d2h_bytes_per_step": int(nz_h.numel() * 8 + b_h.numel() * 8),
                                                 "variant": "every matrix value + rhs out (extfem_values_get)"},
@@ -415,7 +424,7 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "setup_s": {"mesh_host": t_mesh, "upload_adjacency_pattern": t_setup},
-            "checksum_sum_nzval": checksum,
+            "checksum_sum_nzval": checksum, "e2e_vs_resident_max_rel": e2e_vs_resident,
             "phase_ms": {"stiffness_geo": kern_ms[0], "stiffness_gather": kern_ms[1], "rhs_cell": rhs_ms[0], "rhs_gather": rhs_ms[1]},
             "plan": eng.plan_stats(pat, 0),
         }
