@@ -135,6 +135,8 @@ struct Ctx {
     bool fast_enabled = true;   // option "fastpath"
     int nl_cpw = 8, nl_warps = 4; // options "nonlinear_cells_per_warp", "nonlinear_warps_per_cta" of the tensor-core contraction kernel
     bool nl_sparse_jac = true;  // option "nonlinear_sparse_jacobian": the tensor-core nonlinear path moves only the structural non-zeros of J
+    bool nl_point_cache = true; // option "nonlinear_point_cache": nl_point_kernel caches the physical basis values of its point in shared memory
+    bool nl_rowwise = true;     // option "nonlinear_rowwise": Neo-Hooke point kernel with the Jacobian produced row by row (no spills)
     bool gather_warp = true;    // option "gather_warp": generic matrix reduction with one warp (1) / one thread (0) per column
     int nl_version = 4;         // option "nonlinear_kernel": 1 entry-wise local kernel, 2 staged per block, 3 warp per cell,
                                 // 4 warp per cell with the contractions on FP64 tensor cores (falls back to 3 when not applicable)
@@ -1947,6 +1949,8 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "nonlinear_cells_per_warp")) { C->nl_cpw = std::min(std::max(value, 1), 1024); return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_warps_per_cta")) { C->nl_warps = std::min(std::max(value, 1), 4); return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_sparse_jacobian")) { C->nl_sparse_jac = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "nonlinear_point_cache")) { C->nl_point_cache = value != 0; return EXTFEM_OK; }
+    if (key && !strcmp(key, "nonlinear_rowwise")) { C->nl_rowwise = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "gather_warp")) { C->gather_warp = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_kernel")) { C->nl_version = std::min(std::max(value, 1), 4); return EXTFEM_OK; }
     if (key && !strcmp(key, "fastpath_templates")) { C->tmpl_enabled = value != 0; return EXTFEM_OK; }
@@ -2454,11 +2458,24 @@ int extfem_assemble_nonlinear(extfem_ctx *ctx, int pattern, const extfem_opdesc 
                 double *wJ = C->nlpt.as<double>(), *rqg = wJ + (size_t)ntot * T3.nnzJ;
                 // (1) kernel value and Jacobian per (cell, point), one thread each
                 const unsigned gp = nblocks(ntot, 128);
+                // physical basis values of a thread cached in shared memory when they fit (kernels_generic.cuh: PVC)
+                const int npv = T3.phi_off[T3.nspaces] / op.nq;
+                const bool pvc = C->nl_point_cache && npv < 65536 && nl_point_smem(T3.tab_bytes, op.nq, op.NC, T3.EC, npv, true) <= 72 * 1024;
+                const size_t psm = nl_point_smem(T3.tab_bytes, op.nq, op.NC, T3.EC, npv, pvc);
                 switch (op.nin) {
-#define EXTFEM_NLPT(N) case N: smem_attr(C, (const void *)nl_point_kernel<DIM, N>, 200 * 1024); \
-                       nl_point_kernel<DIM, N><<<gp, 128, T3.tab_bytes + (size_t)(128 / op.nq + 2) * op.NC * 8, C->stream>>>(op, T3, wJ, rqg); break;
-                EXTFEM_NLPT(2) EXTFEM_NLPT(3) EXTFEM_NLPT(4) EXTFEM_NLPT(7) EXTFEM_NLPT(9)
+#define EXTFEM_NLPT2(D, N, R, P) { smem_attr(C, (const void *)nl_point_kernel<D, N, R, P>, 200 * 1024); \
+                                   nl_point_kernel<D, N, R, P><<<gp, 128, psm, C->stream>>>(op, T3, wJ, rqg); }
+#define EXTFEM_NLPT(N) case N: if (pvc) EXTFEM_NLPT2(DIM, N, false, true) else EXTFEM_NLPT2(DIM, N, false, false) break;
+                EXTFEM_NLPT(2) EXTFEM_NLPT(3) EXTFEM_NLPT(4) EXTFEM_NLPT(7)
+                case 9:
+                    if (DIM == 3 && op.kernel_id == EXTFEM_NL_NEOHOOKE3D && C->nl_rowwise) {   // Jacobian row by row: no spills
+                        if (pvc) EXTFEM_NLPT2(3, 9, true, true) else EXTFEM_NLPT2(3, 9, true, false)
+                    } else {
+                        if (pvc) EXTFEM_NLPT2(DIM, 9, false, true) else EXTFEM_NLPT2(DIM, 9, false, false)
+                    }
+                    break;
 #undef EXTFEM_NLPT
+#undef EXTFEM_NLPT2
                 }
                 ++C->launches;
                 // (2) contractions on the FP64 tensor cores, one warp per cell: k-steps / rank-1 remainder by the kernel's vector length

@@ -945,8 +945,86 @@ __device__ __forceinline__ void nl_apply_fixed(int id, const double (&u)[NIO], c
     }
 }
 
-template <int DIM, int NIO>
-__global__ void __launch_bounds__(128, 3)
+// Neo-Hooke (EXTFEM_NL_NEOHOOKE3D in nl_apply) with the Jacobian produced ROW BY ROW.  In the array form all 81 entries of D2W are
+// computed before the first one is stored (the store loop is a chain of conditional blocks the compiler does not sink them
+// into): nl_point_kernel<3, 9> needed 168 registers plus 392 bytes of spills, ~480 local-memory loads per point
+// (profiles/r02_ncu_nl_point_config4.txt).  Same formulas and operation order as the array form.
+struct NeoState {
+    double F[9], dd[9], mu, c, e;
+};
+
+__device__ __forceinline__ void neo_prepare(const double (&in)[9], const double *p, NeoState &S, double (&val)[9])
+{
+    const double mu = p[0], la = p[1];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) S.F[i] = in[i];
+    S.F[0] += 1.0; S.F[4] += 1.0; S.F[8] += 1.0;
+    const double (&F)[9] = S.F;
+    S.dd[0] = F[4] * F[8] - F[5] * F[7];
+    S.dd[1] = F[5] * F[6] - F[3] * F[8];
+    S.dd[2] = F[3] * F[7] - F[4] * F[6];
+    S.dd[3] = F[2] * F[7] - F[1] * F[8];
+    S.dd[4] = F[0] * F[8] - F[2] * F[6];
+    S.dd[5] = F[1] * F[6] - F[0] * F[7];
+    S.dd[6] = F[1] * F[5] - F[2] * F[4];
+    S.dd[7] = F[2] * F[3] - F[0] * F[5];
+    S.dd[8] = F[0] * F[4] - F[1] * F[3];
+    const double det = F[0] * S.dd[0] + F[1] * S.dd[1] + F[2] * S.dd[2];
+    const double ld = log(det);
+    S.mu = mu;
+    S.c = (la * ld - mu) / det;
+    S.e = (la + mu - la * ld) / (det * det);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) val[i] = mu * F[i] + S.c * S.dd[i];
+}
+
+// d(dd_i)/dF_j of the cofactor matrix dd: sign * (k + 1) for +-F[k], 0 for none (the EXTFEM_D2 list of nl_apply as a table)
+__host__ __device__ constexpr int neo_d2(int i, int j)
+{
+    constexpr int T[9][8] = {{4, 9, 8, 5, 5, -8, 7, -6}, {5, 7, 6, 6, 3, -9, 8, -4}, {3, 8, 7, 4, 4, -7, 6, -5},
+                             {2, 8, 7, 3, 1, -9, 8, -2}, {0, 9, 8, 1, 2, -7, 6, -3}, {1, 7, 6, 2, 0, -8, 7, -1},
+                             {1, 6, 5, 2, 2, -5, 4, -3}, {2, 4, 3, 3, 0, -6, 5, -1}, {0, 5, 4, 1, 1, -4, 3, -2}};
+    for (int q = 0; q < 4; ++q)
+        if (T[i][2 * q] == j) return T[i][2 * q + 1];
+    return 0;
+}
+
+template <int I, int J_>
+__device__ __forceinline__ double neo_entry(const NeoState &S)
+{
+    constexpr int d = neo_d2(I, J_);
+    double v = S.e * S.dd[I] * S.dd[J_];
+    if (I == J_) v += S.mu;
+    if (d > 0) v += S.c * S.F[d > 0 ? d - 1 : 0];
+    if (d < 0) v += -S.c * S.F[d < 0 ? -d - 1 : 0];
+    return v;
+}
+
+template <int I>
+__device__ __forceinline__ void neo_row(const NeoState &S, double (&row)[9])
+{
+    row[0] = neo_entry<I, 0>(S); row[1] = neo_entry<I, 1>(S); row[2] = neo_entry<I, 2>(S);
+    row[3] = neo_entry<I, 3>(S); row[4] = neo_entry<I, 4>(S); row[5] = neo_entry<I, 5>(S);
+    row[6] = neo_entry<I, 6>(S); row[7] = neo_entry<I, 7>(S); row[8] = neo_entry<I, 8>(S);
+}
+
+// shared memory of nl_point_kernel: tables | solution coefficients of the block's cells | (PVC) u16 index of every B entry into
+// the thread's physical basis values | (PVC) the values [entry][thread]
+__host__ __device__ inline size_t nl_point_smem(int tab_bytes, int nq, int NC, int EC, int npv, bool pvc)
+{
+    size_t b = (size_t)tab_bytes + (size_t)(128 / nq + 2) * NC * 8;
+    if (pvc) b += ((size_t)EC * NC * 2 + 15) / 16 * 16 + (size_t)npv * 128 * 8;
+    return b;
+}
+
+// ROW: the row-wise flavour of a registered kernel (Neo-Hooke, NIO = 9).
+// PVC: every thread first evaluates the physical basis values of its (cell, point) -- value and DIM physical derivatives of every
+// scalar basis function of every space, the PHI layout of the contraction kernel -- into its column of a shared array; the
+// input_args loop then costs one shared load per (dof, entry) pair.  Without it every pair fetches its reference gradient, picks
+// a column of A^-1 (which the compiler turns into a dynamically indexed local-memory array) and transforms it: three times the
+// work for vector-valued spaces and ~65 instructions per pair (8000 per point at config 4).
+template <int DIM, int NIO, bool ROW, bool PVC>
+__global__ void __launch_bounds__(128, ROW ? 4 : 3)
 nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tables T, double *__restrict__ wJ, double *__restrict__ rqg)
 {
     extern __shared__ __align__(16) unsigned char tb[];
@@ -967,6 +1045,16 @@ nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tab
         while (b + 1 < T.ncolblocks && j >= T.blk_locoff[b] + T.blk_nd[b]) ++b;
         solc[i] = op.sol[T.blk_soloff[b] + T.blk_celldofs[b][(c0 + c) * T.blk_nd[b] + (j - T.blk_locoff[b])]];
     }
+    unsigned short *pidx = reinterpret_cast<unsigned short *>(solc + (size_t)(128 / nq + 2) * NC);
+    double *pv = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(pidx) + ((size_t)T.EC * NC * 2 + 15) / 16 * 16) + threadIdx.x;
+    if constexpr (PVC) {
+        __syncthreads();    // the tables (pt) are complete
+        // B entry (x, j) -> index of its physical basis value: (values before this space) + k (1 + DIM) + source
+        for (int i = threadIdx.x; i < T.EC * NC; i += blockDim.x) {
+            const uchar4 e = pt[i];
+            pidx[i] = (unsigned short)(T.phi_off[e.x] / nq + e.y * (1 + DIM) + e.z);
+        }
+    }
     __syncthreads();
     if (t >= ntot) return;
     const long long cell = t / nq;
@@ -974,6 +1062,26 @@ nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tab
     const double *sc_ = solc + (size_t)(cell - c0) * NC;
     CellGeo<DIM> G;
     load_geo<DIM>(op, cell, G);
+    if constexpr (PVC) {
+        for (int s = 0; s < T.nspaces; ++s) {
+            const int ns = T.ns[s];
+            const double *rv = T.refvals[s] + (size_t)q * ns, *rg = T.refgrads[s] + (size_t)q * ns * DIM;
+            double *dst = pv + (size_t)(T.phi_off[s] / nq) * 128;
+            for (int k = 0; k < ns; ++k, dst += (1 + DIM) * 128) {
+                dst[0] = __ldg(rv + k);
+                double r_[DIM];
+#pragma unroll
+                for (int r = 0; r < DIM; ++r) r_[r] = __ldg(rg + k * DIM + r);
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int r = 0; r < DIM; ++r) v = fma(G.Ainv[r * DIM + d], r_[r], v);
+                    dst[(1 + d) * 128] = v;
+                }
+            }
+        }
+    }
     // input_args: for every component o the (dof, entry) pairs that feed it (static register index)
     double u[NIO];
 #pragma unroll
@@ -981,6 +1089,11 @@ nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tab
         double a = 0.0;
         for (int p = uptr[o]; p < uptr[o + 1]; ++p) {
             const int j = ulist[p] & 0xff, x = ulist[p] >> 8;
+            if constexpr (PVC) {
+                const int i = x * NC + j;
+                a = fma(sc_[j] * bgsc[i], pv[(size_t)pidx[i] * 128], a);
+                continue;
+            }
             const uchar4 e = pt[x * NC + j];
             double v;
             if (e.z == 0) v = __ldg(T.refvals[e.x] + q * T.ns[e.x] + e.y);
@@ -1001,9 +1114,30 @@ nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tab
         }
         u[o] = a;
     }
+    const double w = op.qw[q], sc = op.factor * w * G.vol;
+    if constexpr (ROW && NIO == 9) {
+        double val[9];
+        NeoState S;
+        neo_prepare(u, op.params, S, val);
+#define EXTFEM_NEO_ROW(K)                                                                    \
+        {                                                                                    \
+            double row[9];                                                                   \
+            neo_row<K>(S, row);                                                              \
+            double sum = 0.0;                                                                \
+            _Pragma("unroll") for (int d = 0; d < 9; ++d) {                                  \
+                sum = fma(row[d], u[d], sum);                                                \
+                const int sl = jslot[K * 9 + d];                                             \
+                if (sl != 255) wJ[(size_t)sl * ntot + t] = row[d] * w;                       \
+            }                                                                                \
+            rqg[(size_t)K * ntot + t] = (sum - val[K]) * sc;                                 \
+        }
+        EXTFEM_NEO_ROW(0) EXTFEM_NEO_ROW(1) EXTFEM_NEO_ROW(2) EXTFEM_NEO_ROW(3) EXTFEM_NEO_ROW(4)
+        EXTFEM_NEO_ROW(5) EXTFEM_NEO_ROW(6) EXTFEM_NEO_ROW(7) EXTFEM_NEO_ROW(8)
+#undef EXTFEM_NEO_ROW
+        return;
+    }
     double val[NIO], J[NIO * NIO];
     nl_apply_fixed<DIM, NIO>(op.kernel_id, u, op.params, val, J, op.cellregions[cell]);
-    const double w = op.qw[q], sc = op.factor * w * G.vol;
 #pragma unroll
     for (int k = 0; k < NIO; ++k) {
         double sum = 0.0;

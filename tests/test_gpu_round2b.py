@@ -185,3 +185,56 @@ def test_lower_triangle_export_pipelined(pkg, engine):
     lz_pin = torch.empty(n, dtype=torch.float64).pin_memory(); lb_pin = torch.empty(F.ndofs, dtype=torch.float64).pin_memory()
     engine.values_get_lower(pat, nzval_out=lz_pin, b_out=lb_pin)
     assert np.array_equal(lz_pin.numpy(), L.data) and np.array_equal(lb_pin.numpy(), b)
+
+
+def _nl_case(pkg, name):
+    """(grid, fetypes, args, registry name, oracle kernel name, params, state) of a Newton assembly on the tensor-core path."""
+    if name == "neohooke_p2":
+        E, nu = 10.0, 0.3
+        X = np.linspace(0, 1, 4)
+        return (pkg.simplexgrid(X, X ** 1.2, X), [pkg.H1P2(3, 3)], [(0, GRAD)], "neohooke3d", "neohooke3d",
+                [E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))],
+                [lambda x: 0.1 * np.stack([x[:, 0] ** 2, x[:, 0] + x[:, 1], x[:, 1] * x[:, 2]], axis=1)])
+    if name == "neohooke_p1":
+        E, nu = 10.0, 0.3
+        X = np.linspace(0, 1, 5)
+        return (pkg.simplexgrid(X, X, X ** 0.9), [pkg.H1Pk(3, 3, 1)], [(0, GRAD)], "neohooke3d", "neohooke3d",
+                [E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))],
+                [lambda x: 0.1 * np.stack([x[:, 0] * x[:, 2], x[:, 0] - x[:, 1], x[:, 1] ** 2], axis=1)])
+    if name == "nse2d":
+        return (pkg.uniform_refine(pkg.grid_unitsquare(), 3), [pkg.H1P2(2, 2), pkg.H1P1(1)], [(0, 0), (0, GRAD), (1, 0)], "nse2d", "nse2d",
+                [0.05], [lambda x: np.stack([x[:, 0] ** 2, x[:, 0] + x[:, 1]], axis=1), lambda x: x[:, 1] ** 2])
+    X = np.linspace(0, 1, 13)
+    return (pkg.simplexgrid(X, X ** 1.3), [pkg.H1P2(1, 2)], [(0, 0), (0, GRAD)], "rcd", "rcd", [],
+            [lambda x: np.sin(2 * x[:, 0]) + x[:, 1] ** 2])
+
+
+@pytest.mark.parametrize("case", ["neohooke_p2", "neohooke_p1", "nse2d", "rcd"])
+def test_nonlinear_point_kernel_variants(pkg, ora, engine, case):
+    """nl_point_kernel with and without the shared-memory cache of the physical basis values (`nonlinear_point_cache`) and, for
+    Neo-Hooke, with the Jacobian produced row by row (`nonlinear_rowwise`): all against the oracle, and bit-identical to each
+    other (same formulas in the same order)."""
+    g, fet, args, kern, okern, params, state = _nl_case(pkg, case)
+    S = System(pkg, ora, engine, g, fet)
+    u = pkg.FEVector(S.FES)
+    for blk, f in enumerate(state):
+        pkg.interpolate(u[blk], f)
+    sol = u.entries
+    d = engine.make_opdesc(args, args=args, kernel_id=pkg.lib.kernel_id(kern), params=params)
+    nzref, bref = ora.assemble_nonlinear(S.omesh, S.oargs(args), S.oargs(args), sol, np.zeros(S.N), okern, params=params,
+                                         csc=(S.colptr, S.rowval))
+    got = {}
+    try:
+        for cache, row in ((1, 1), (0, 1), (1, 0), (0, 0)):
+            engine.set_option("nonlinear_point_cache", cache)
+            engine.set_option("nonlinear_rowwise", row)
+            nz = np.empty(S.rowval.size); b = np.empty(S.N)
+            engine.assemble_nonlinear(S.pat, d, sol, nzval_out=nz, b_out=b)
+            check_values(nz, nzref, what=f"jacobian cache={cache} rowwise={row}")
+            check_values(b, bref, scale=np.abs(bref).max() + np.abs(nzref).max() * np.abs(sol).max(), what=f"newton rhs cache={cache} rowwise={row}")
+            got[(cache, row)] = (nz, b)
+        for key in ((0, 1), (1, 0), (0, 0)):
+            assert np.array_equal(got[(1, 1)][0], got[key][0]) and np.array_equal(got[(1, 1)][1], got[key][1]), key
+    finally:
+        engine.set_option("nonlinear_point_cache", 1)
+        engine.set_option("nonlinear_rowwise", 1)
