@@ -136,7 +136,6 @@ struct Ctx {
     int nl_cpw = 8, nl_warps = 4; // options "nonlinear_cells_per_warp", "nonlinear_warps_per_cta" of the tensor-core contraction kernel
     bool nl_sparse_jac = true;  // option "nonlinear_sparse_jacobian": the tensor-core nonlinear path moves only the structural non-zeros of J
     bool nl_point_cache = true; // option "nonlinear_point_cache": nl_point_kernel caches the physical basis values of its point in shared memory
-    bool nl_const_jac = true;   // option "nonlinear_const_jacobian": Jacobian entries with the same value at every state do not travel
     bool nl_rowwise = true;     // option "nonlinear_rowwise": Neo-Hooke point kernel with the Jacobian produced row by row (no spills)
     bool gather_warp = true;    // option "gather_warp": generic matrix reduction with one warp (1) / one thread (0) per column
     int nl_version = 4;         // option "nonlinear_kernel": 1 entry-wise local kernel, 2 staged per block, 3 warp per cell,
@@ -1520,41 +1519,20 @@ static int build_nl3_tables(Ctx *ctx, const OpDev &op, NL3Tables &T, bool *ok, b
                      nl4_warp_doubles(op.nq, op.nin, op.nin * op.nout, T.Np4, off) * 8 * 4 <= 120 * 1024;
         // structural non-zeros of the kernel's Jacobian (probed on the device with the operator's parameters)
         T.nnzJ = op.nin * op.nout;
-        T.nvarJ = T.nnzJ;
         T.o_jslot = reserve((size_t)op.nin * op.nout);
         for (int e = 0; e < op.nin * op.nout; ++e) host[T.o_jslot + e] = (unsigned char)e;
-        T.o_jconst = reserve(8);
         if (want_dense && T.dense_ok && ctx->nl_sparse_jac) {
-            // probe: which entries are structurally zero, which have the same value at every state (they do not travel either:
-            // the contraction kernel writes w_q times the constant once per warp)
-            const size_t ne = (size_t)op.nin * op.nout;
             DevBuf dm;
-            std::vector<unsigned char> hm(2 * ne);
-            std::vector<double> hv(ne);
-            if (int rc = ensure(ctx, dm, 2 * ne + 16 + ne * 8)) return rc;
-            double *dv = reinterpret_cast<double *>(dm.as<unsigned char>() + (2 * ne + 15) / 16 * 16);
-            EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(dm.p, 0, 2 * ne + 16 + ne * 8, ctx->stream));
-            nl_mask_kernel<<<1, 32, 0, ctx->stream>>>(op, op.dim, dm.as<unsigned char>(), dm.as<unsigned char>() + ne, dv);
+            std::vector<unsigned char> hm((size_t)op.nin * op.nout);
+            if (int rc = ensure(ctx, dm, hm.size())) return rc;
+            EXTFEM_CUDA_CHECK(ctx, cudaMemsetAsync(dm.p, 0, hm.size(), ctx->stream));
+            nl_mask_kernel<<<1, 32, 0, ctx->stream>>>(op, op.dim, dm.as<unsigned char>());
             LAUNCHED(ctx);
-            EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(hm.data(), dm.p, 2 * ne, cudaMemcpyDeviceToHost, ctx->stream));
-            EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(hv.data(), dv, ne * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            EXTFEM_CUDA_CHECK(ctx, cudaMemcpyAsync(hm.data(), dm.p, hm.size(), cudaMemcpyDeviceToHost, ctx->stream));
             EXTFEM_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-            int nv = 0, n = 0;
-            std::vector<double> consts;
-            for (size_t e = 0; e < ne; ++e) {
-                const bool isc = ctx->nl_const_jac && hm[ne + e];
-                if (hm[e] && !isc) host[T.o_jslot + e] = (unsigned char)nv++;
-            }
-            n = nv;
-            for (size_t e = 0; e < ne; ++e) {
-                const bool isc = ctx->nl_const_jac && hm[ne + e];
-                if (!hm[e]) host[T.o_jslot + e] = (unsigned char)255;
-                else if (isc) { host[T.o_jslot + e] = (unsigned char)n++; consts.push_back(hv[e]); }
-            }
+            int n = 0;
+            for (size_t e = 0; e < hm.size(); ++e) host[T.o_jslot + e] = hm[e] ? (unsigned char)n++ : (unsigned char)255;
             T.nnzJ = std::max(n, 1);
-            T.nvarJ = nv;
-            T.o_jconst = reserve(std::max<size_t>(consts.size(), 1) * 8);
-            if (!consts.empty()) memcpy(host.data() + T.o_jconst, consts.data(), consts.size() * 8);
         }
         T.o_pt = reserve((size_t)T.EC * op.NC * 4);
         for (int x = 0; x < T.EC; ++x)
@@ -1972,7 +1950,6 @@ int extfem_set_option(extfem_ctx *ctx, const char *key, int value)
     if (key && !strcmp(key, "nonlinear_warps_per_cta")) { C->nl_warps = std::min(std::max(value, 1), 4); return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_sparse_jacobian")) { C->nl_sparse_jac = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_point_cache")) { C->nl_point_cache = value != 0; return EXTFEM_OK; }
-    if (key && !strcmp(key, "nonlinear_const_jacobian")) { C->nl_const_jac = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_rowwise")) { C->nl_rowwise = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "gather_warp")) { C->gather_warp = value != 0; return EXTFEM_OK; }
     if (key && !strcmp(key, "nonlinear_kernel")) { C->nl_version = std::min(std::max(value, 1), 4); return EXTFEM_OK; }

@@ -753,8 +753,6 @@ struct NL3Tables {
     int dense_ok, NT4, Np4;                    // tensor-core path: number of 8-wide dof tiles and the row stride of B_q
     int o_ddst;                                // u16 [EC][NC]: offset of the sparse entry inside the dense B_q
     int nnzJ, o_jslot;                         // structurally non-zero Jacobian entries; u8 [nout*nin] compact slot or 255
-    int nvarJ, o_jconst;                       // slots < nvarJ depend on the state and travel per point; slots nvarJ .. nnzJ-1 hold
-                                               // the same value at every state (f64 [nnzJ - nvarJ] in the table buffer)
     int o_pt;                                  // u8x4 [EC][NC]: (space, scalar basis function, source 0 value | 1+d gradient, -) of a B entry
     int nspaces, ns[NL2_MAXSP_];
     const double *refvals[NL2_MAXSP_], *refgrads[NL2_MAXSP_];
@@ -919,8 +917,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 
 // Structural non-zeros of a registered kernel's Jacobian for the operator's parameters: 32 probes at random states (all regions
 // the material tables distinguish); an entry that is zero in every probe is never stored or multiplied.
-__global__ void nl_mask_kernel(const __grid_constant__ OpDev op, int dim, unsigned char *__restrict__ mask, unsigned char *__restrict__ isconst,
-                               double *__restrict__ cval)
+__global__ void nl_mask_kernel(const __grid_constant__ OpDev op, int dim, unsigned char *__restrict__ mask)
 {
     double in[16], val[16], J[256];
     unsigned s = threadIdx.x * 2654435761u + 12345u;
@@ -929,13 +926,8 @@ __global__ void nl_mask_kernel(const __grid_constant__ OpDev op, int dim, unsign
         in[i] = ((s >> 8) & 0xffffu) / 65536.0 * 1.5 + 0.25;
     }
     nl_apply(op.kernel_id, dim, in, op.params, val, J, op.nin, op.nout, 1 + (threadIdx.x & 7));
-    for (int e = 0; e < op.nin * op.nout; ++e) {
+    for (int e = 0; e < op.nin * op.nout; ++e)
         if (J[e] != 0.0) mask[e] = 1;
-        // the same bits at all 32 states (and in all probed regions): the entry does not depend on the state
-        const double v0 = __shfl_sync(0xffffffffu, J[e], 0);
-        const bool same = __all_sync(0xffffffffu, J[e] == v0);
-        if (threadIdx.x == 0) { isconst[e] = same ? 1 : 0; cval[e] = v0; }
-    }
 }
 
 // nl_apply with compile-time vector lengths and the kernel id folded per case: after inlining every index is static, the value and
@@ -1123,7 +1115,6 @@ nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tab
         u[o] = a;
     }
     const double w = op.qw[q], sc = op.factor * w * G.vol;
-    const int nvar = T.nvarJ;      // structural zeros (255) and state-independent entries (slots >= nvar) are not stored
     if constexpr (ROW && NIO == 9) {
         double val[9];
         NeoState S;
@@ -1136,7 +1127,7 @@ nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tab
             _Pragma("unroll") for (int d = 0; d < 9; ++d) {                                  \
                 sum = fma(row[d], u[d], sum);                                                \
                 const int sl = jslot[K * 9 + d];                                             \
-                if (sl < nvar) wJ[(size_t)sl * ntot + t] = row[d] * w;                       \
+                if (sl != 255) wJ[(size_t)sl * ntot + t] = row[d] * w;                       \
             }                                                                                \
             rqg[(size_t)K * ntot + t] = (sum - val[K]) * sc;                                 \
         }
@@ -1154,7 +1145,7 @@ nl_point_kernel(const __grid_constant__ OpDev op, const __grid_constant__ NL3Tab
         for (int d = 0; d < NIO; ++d) {
             sum = fma(J[k * NIO + d], u[d], sum);
             const int sl = jslot[k * NIO + d];        // structural zeros of the Jacobian are not stored
-            if (sl < nvar) wJ[(size_t)sl * ntot + t] = J[k * NIO + d] * w;
+            if (sl != 255) wJ[(size_t)sl * ntot + t] = J[k * NIO + d] * w;
         }
         rqg[(size_t)k * ntot + t] = (sum - val[k]) * sc;
     }
@@ -1202,14 +1193,6 @@ local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant_
     double *j8 = rq + (size_t)nq * nin;        // [nin] last Jacobian row of the current point, dense (R1)
     for (int i = lane; i < 2 * rows * Np; i += 32) Bq[i] = 0.0;   // structural zeros and padding stay zero for every cell and point
     __syncthreads();
-    const int JV = T.nvarJ;                    // slots below JV arrive per point; the others are w_q times a constant, written once
-    {
-        const double *jconst = reinterpret_cast<const double *>(tb + T.o_jconst);
-        for (int i = lane; i < (JS - JV) * nq; i += 32) {
-            const int e = i / nq, q = i - e * nq;
-            Jq[q * JS + JV + e] = jconst[e] * op.qw[q];
-        }
-    }
     const int gid = lane >> 2, tig = lane & 3;
     // compact slots of this lane's Jacobian fragment (rows gid [+8], columns 4 ks + tig, and the rank-1 column): -1 = structural zero
     int sa[MT][KS], sr[MT];
@@ -1259,7 +1242,7 @@ local_nonlinear_kernel4(const __grid_constant__ OpDev op, const __grid_constant_
             const double *wJc = wJ + cell * nq, *rqc = rqg + cell * nq;
             const int de = 32 / nq, dq = 32 - de * nq;
             int e = lane / nq, q = lane - e * nq;
-            for (int i = lane; i < JV * nq; i += 32) {
+            for (int i = lane; i < JS * nq; i += 32) {
                 Jq[q * JS + e] = __ldg(wJc + (size_t)e * ntot + q);
                 e += de; q += dq;
                 if (q >= nq) { q -= nq; ++e; }

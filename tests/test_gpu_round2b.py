@@ -201,9 +201,6 @@ def _nl_case(pkg, name):
         return (pkg.simplexgrid(X, X, X ** 0.9), [pkg.H1Pk(3, 3, 1)], [(0, GRAD)], "neohooke3d", "neohooke3d",
                 [E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))],
                 [lambda x: 0.1 * np.stack([x[:, 0] * x[:, 2], x[:, 0] - x[:, 1], x[:, 1] ** 2], axis=1)])
-    if name == "linnse7":      # Jacobian independent of the state: nothing but the residual terms travels between the kernels
-        return (pkg.uniform_refine(pkg.grid_unitsquare(), 3), [pkg.H1P2(2, 2), pkg.H1P1(1)], [(0, 0), (0, GRAD), (1, 0)], "nl_linnse7", "linnse7",
-                [0.1, 2.0], [lambda x: np.stack([x[:, 0] ** 2, x[:, 0] + x[:, 1]], axis=1), lambda x: x[:, 1] ** 2])
     if name == "nse2d":
         return (pkg.uniform_refine(pkg.grid_unitsquare(), 3), [pkg.H1P2(2, 2), pkg.H1P1(1)], [(0, 0), (0, GRAD), (1, 0)], "nse2d", "nse2d",
                 [0.05], [lambda x: np.stack([x[:, 0] ** 2, x[:, 0] + x[:, 1]], axis=1), lambda x: x[:, 1] ** 2])
@@ -212,11 +209,10 @@ def _nl_case(pkg, name):
             [lambda x: np.sin(2 * x[:, 0]) + x[:, 1] ** 2])
 
 
-@pytest.mark.parametrize("case", ["neohooke_p2", "neohooke_p1", "nse2d", "linnse7", "rcd"])
+@pytest.mark.parametrize("case", ["neohooke_p2", "neohooke_p1", "nse2d", "rcd"])
 def test_nonlinear_point_kernel_variants(pkg, ora, engine, case):
-    """nl_point_kernel with and without the shared-memory cache of the physical basis values (`nonlinear_point_cache`), for
-    Neo-Hooke with the Jacobian produced row by row (`nonlinear_rowwise`), and with / without the state-independent Jacobian
-    entries travelling between the two kernels (`nonlinear_const_jacobian`): all against the oracle, and bit-identical to each
+    """nl_point_kernel with and without the shared-memory cache of the physical basis values (`nonlinear_point_cache`) and, for
+    Neo-Hooke, with the Jacobian produced row by row (`nonlinear_rowwise`): all against the oracle, and bit-identical to each
     other (same formulas in the same order)."""
     g, fet, args, kern, okern, params, state = _nl_case(pkg, case)
     S = System(pkg, ora, engine, g, fet)
@@ -229,20 +225,16 @@ def test_nonlinear_point_kernel_variants(pkg, ora, engine, case):
                                          csc=(S.colptr, S.rowval))
     got = {}
     try:
-        for cache, row, cj in ((1, 1, 1), (0, 1, 1), (1, 0, 1), (0, 0, 1), (1, 1, 0), (0, 0, 0)):
+        for cache, row in ((1, 1), (0, 1), (1, 0), (0, 0)):
             engine.set_option("nonlinear_point_cache", cache)
             engine.set_option("nonlinear_rowwise", row)
-            engine.set_option("nonlinear_const_jacobian", cj)
-            # the tables of an operator are built per assembly, so the options take effect at once
             nz = np.empty(S.rowval.size); b = np.empty(S.N)
             engine.assemble_nonlinear(S.pat, d, sol, nzval_out=nz, b_out=b)
-            check_values(nz, nzref, what=f"jacobian cache={cache} rowwise={row} const={cj}")
-            check_values(b, bref, scale=np.abs(bref).max() + np.abs(nzref).max() * np.abs(sol).max(),
-                         what=f"newton rhs cache={cache} rowwise={row} const={cj}")
-            got[(cache, row, cj)] = (nz, b)
-        for key in list(got)[1:]:
-            assert np.array_equal(got[(1, 1, 1)][0], got[key][0]) and np.array_equal(got[(1, 1, 1)][1], got[key][1]), key
+            check_values(nz, nzref, what=f"jacobian cache={cache} rowwise={row}")
+            check_values(b, bref, scale=np.abs(bref).max() + np.abs(nzref).max() * np.abs(sol).max(), what=f"newton rhs cache={cache} rowwise={row}")
+            got[(cache, row)] = (nz, b)
+        for key in ((0, 1), (1, 0), (0, 0)):
+            assert np.array_equal(got[(1, 1)][0], got[key][0]) and np.array_equal(got[(1, 1)][1], got[key][1]), key
     finally:
         engine.set_option("nonlinear_point_cache", 1)
         engine.set_option("nonlinear_rowwise", 1)
-        engine.set_option("nonlinear_const_jacobian", 1)
